@@ -1,0 +1,508 @@
+// K2 (exact engine): fused dot-product scores + train mask + top-K, fp32 CUDA cores.
+//
+// Replaces the body of gene_ranklist (Model/LightGCN.py:137-162: torch.matmul -> python mask
+// loop -> torch.topk) and, with row-normalised features on both sides, the sim + topk of the
+// kNN builders (Model/FREEDOM.py:114-118, Model/LATTICE.py:46-48, gen_hypergraph_u_i.py:41-46).
+// The score matrix only ever exists as 8x8 register tiles.
+//
+// Structure (one persistent CTA per resident slot, 2 per SM when d <= 64):
+//   * a CTA owns a tile of 128 rows of A (users) taken from an atomic tile counter and streams
+//     all of B (items) through a 2-stage shared-memory ring in tiles of 128 rows x 64 floats;
+//     the ring is filled by descriptor-less TMA row copies (cp.async.bulk -> mbarrier
+//     complete_tx) into rows padded to 68 floats, which makes every LDS.128 of the 4x8 lane
+//     layout bank-conflict free;
+//   * each thread accumulates an 8x8 tile; every (row, col) score is the canonical fp32 chain
+//     acc = fmaf(a[k], b[k], acc), k ascending, so results are bit-identical to oracle/canon.c;
+//   * epilogue: one FSETP per score against the row's current K-th best; survivors (a few per
+//     thousand) take a slow path: exact 64-bit key compare, binary search in the row's train
+//     mask (masked items are dropped here and re-enter at the end with mask_value), append to
+//     the row's candidate list (L2-resident workspace);
+//   * when a list passes CAP - 128 entries a warp sorts it (bitonic, in the just-freed ring
+//     stage) and keeps the best K, raising the row threshold;
+//   * after the last tile the first K masked items (score = mask_value) are merged in, the list
+//     is sorted by (score desc, index asc) and the top K leave as int64 ids (+ id_offset).
+#include "common.cuh"
+
+namespace chaorec {
+namespace {
+
+constexpr int TU = 128;            // A rows per CTA tile
+constexpr int TI = 128;            // B rows per ring stage
+constexpr int KC = 64;             // floats of the contraction dimension per stage
+constexpr int LDSF = KC + 4;       // padded row stride in floats (272 B)
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int CAP = 256;           // candidate slots per row
+constexpr int kTrigger = CAP - TI; // a tile can add at most TI entries to a row
+constexpr int kMaxK = 64;
+constexpr int kTileFloats = TU * LDSF;                 // one 128 x 68 tile
+constexpr int kTileBytes = kTileFloats * 4;            // 34816
+constexpr int kScratchKeys = kTileBytes / kWarps / 8;  // 544 keys of sort scratch per warp
+
+struct RankArgs {
+    const float *A;
+    const float *B;
+    int64_t Ma, Nb;
+    int d;
+    int K;
+    const int64_t *mask_rowptr;
+    const int32_t *mask_col;
+    float mask_value;
+    int exclude_self;
+    int64_t self_off;  // row r of A is column r + self_off of B
+    int64_t id_offset;
+    int64_t *out_idx;
+    float *out_score;
+    uint64_t *cand;  // [gridDim.x][TU][CAP]
+    unsigned int *tile_counter;
+    int n_row_tiles;
+};
+
+struct RowState {
+    float tau_f[TU];
+    int cnt[TU];
+    uint64_t tau_key[TU];
+};
+
+// ---- warp-level bitonic sort, descending, P a power of two, data in shared memory -----------
+__device__ __forceinline__ void warp_sort_desc(uint64_t *s, int P, int lane) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (P >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool desc = ((i & k) == 0);
+                const uint64_t a = s[i], b = s[l];
+                if ((a < b) == desc && a != b) {
+                    s[i] = b;
+                    s[l] = a;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__device__ __forceinline__ int next_pow2_min64(int n) {
+    int p = 64;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// Slow path of the epilogue: called for the few scores that pass the float threshold.
+// Returns 1 when the row's list has grown past the merge trigger.
+__device__ __noinline__ int try_append(const RankArgs *__restrict__ ap, RowState *st, uint64_t *cand_cta, int ul,
+                                       int64_t u, int64_t item, float s) {
+    const RankArgs &a = *ap;  // shared-memory copy of the kernel arguments
+    if (item >= a.Nb) return 0;
+    if (a.exclude_self && item == u + a.self_off) return 0;
+    const uint64_t key = make_key(s, static_cast<uint32_t>(item));
+    if (key <= st->tau_key[ul]) return 0;
+    if (a.mask_rowptr != nullptr) {
+        int64_t lo = a.mask_rowptr[u], hi = a.mask_rowptr[u + 1];
+        const int32_t want = static_cast<int32_t>(item);
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            const int32_t v = a.mask_col[mid];
+            if (v == want) return 0;  // train item: re-enters at the end with mask_value
+            if (v < want) lo = mid + 1; else hi = mid;
+        }
+    }
+    const int pos = atomicAdd(&st->cnt[ul], 1);
+    if (pos < CAP) cand_cta[static_cast<size_t>(ul) * CAP + pos] = key;
+    return (pos + 1 > kTrigger) ? 1 : 0;
+}
+
+// Keep the best K of row ul's list (sorted, best first) and raise its threshold.
+__device__ __forceinline__ void merge_row(const RankArgs &a, RowState *st, uint64_t *cand_cta, int ul,
+                                          uint64_t *scratch, int lane) {
+    int n = st->cnt[ul];
+    if (n > CAP) n = CAP;
+    const int P = next_pow2_min64(n);
+    uint64_t *row = cand_cta + static_cast<size_t>(ul) * CAP;
+    for (int t = lane; t < P; t += 32) scratch[t] = (t < n) ? row[t] : 0ull;
+    __syncwarp();
+    warp_sort_desc(scratch, P, lane);
+    const int keep = (n < a.K) ? n : a.K;
+    for (int t = lane; t < keep; t += 32) row[t] = scratch[t];
+    if (lane == 0) {
+        st->cnt[ul] = keep;
+        if (n >= a.K) {
+            const uint64_t kth = scratch[a.K - 1];
+            st->tau_key[ul] = kth;
+            st->tau_f[ul] = key_score(kth);
+        }
+    }
+    __syncwarp();
+}
+
+// Final list of a row: candidates + the first K masked items at mask_value, sorted, top K out.
+__device__ __forceinline__ void finish_row(const RankArgs &a, RowState *st, uint64_t *cand_cta, int ul, int64_t u,
+                                           uint64_t *scratch, int lane) {
+    int n = st->cnt[ul];
+    if (n > CAP) n = CAP;
+    int nm = 0;
+    int64_t m_lo = 0;
+    if (a.mask_rowptr != nullptr) {
+        m_lo = a.mask_rowptr[u];
+        const int64_t len = a.mask_rowptr[u + 1] - m_lo;
+        nm = (len < a.K) ? static_cast<int>(len) : a.K;
+    }
+    const int P = next_pow2_min64(n + nm);
+    const uint64_t *row = cand_cta + static_cast<size_t>(ul) * CAP;
+    for (int t = lane; t < P; t += 32) {
+        uint64_t key = 0ull;
+        if (t < n) {
+            key = row[t];
+        } else if (t < n + nm) {
+            const int32_t m = a.mask_col[m_lo + (t - n)];
+            if (m >= 0 && m < a.Nb) key = make_key(a.mask_value, static_cast<uint32_t>(m));
+        }
+        scratch[t] = key;
+    }
+    __syncwarp();
+    warp_sort_desc(scratch, P, lane);
+    for (int t = lane; t < a.K; t += 32) {
+        const uint64_t key = scratch[t];
+        a.out_idx[u * a.K + t] = static_cast<int64_t>(key_index(key)) + a.id_offset;
+        if (a.out_score) a.out_score[u * a.K + t] = key_score(key);
+    }
+    __syncwarp();
+}
+
+// Producer (warp 0): one ring stage = KC-wide slice c of B tile `it` (+ of the A tile when A is
+// not resident).  Rows are copied one by one so that they land on the padded stride.
+template <bool A_RESIDENT>
+__device__ __forceinline__ void issue_stage(const RankArgs &a, float *stage, uint64_t *bar, int64_t u0, int nu,
+                                            int it, int c, int lane) {
+    const int kc = (a.d - c * KC < KC) ? (a.d - c * KC) : KC;
+    const uint32_t row_bytes = static_cast<uint32_t>(kc) * 4u;
+    const int64_t i0 = static_cast<int64_t>(it) * TI;
+    const int nb = (a.Nb - i0 < TI) ? static_cast<int>(a.Nb - i0) : TI;
+    if (lane == 0) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(nb + (A_RESIDENT ? 0 : nu)) * row_bytes);
+    __syncwarp();
+    float *sB = A_RESIDENT ? stage : stage + kTileFloats;
+    for (int r = lane; r < nb; r += 32)
+        bulk_g2s(sB + r * LDSF, a.B + (i0 + r) * a.d + c * KC, row_bytes, bar);
+    if (!A_RESIDENT) {
+        for (int r = lane; r < nu; r += 32)
+            bulk_g2s(stage + r * LDSF, a.A + (u0 + r) * a.d + c * KC, row_bytes, bar);
+    }
+}
+
+template <bool A_RESIDENT>
+__global__ void __launch_bounds__(kThreads, A_RESIDENT ? 2 : 1) rank_topk_kernel(const RankArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [A tile (resident only)] [stage 0] [stage 1] [RowState] [barriers] [tile id]
+    constexpr int kStageFloats = A_RESIDENT ? kTileFloats : 2 * kTileFloats;
+    float *sA_res = reinterpret_cast<float *>(smem_raw);
+    float *stage0 = sA_res + (A_RESIDENT ? kTileFloats : 0);
+    float *stage1 = stage0 + kStageFloats;
+    RowState *st = reinterpret_cast<RowState *>(stage1 + kStageFloats);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(st + 1);  // [0],[1] ring stages, [2] resident A
+    int *s_tile = reinterpret_cast<int *>(bars + 3);
+    __shared__ RankArgs s_args;  // for the out-of-line slow path (avoids a per-thread local copy)
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int wu = warp >> 1;  // 4 warps along rows (32 rows each)
+    const int wi = warp & 1;   // 2 warps along columns (64 columns each)
+    const int ty4 = lane >> 3; // 4 lanes along rows
+    const int tx8 = lane & 7;  // 8 lanes along columns
+    const int urow0 = wu * 32 + ty4;  // + 4*i
+    const int icol0 = wi * 64 + tx8;  // + 8*j
+
+    // zero the tiles once so that never-written rows of edge tiles hold finite values
+    {
+        float4 *z = reinterpret_cast<float4 *>(smem_raw);
+        const int n4 = ((A_RESIDENT ? 3 : 4) * kTileBytes) / 16;
+        for (int t = tid; t < n4; t += kThreads) z[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid == 0) {
+        s_args = a;
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
+        mbar_fence_init();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    uint64_t *cand_cta = a.cand + static_cast<size_t>(blockIdx.x) * TU * CAP;
+    uint32_t ph0 = 0, ph1 = 0, phA = 0;
+    const int nch = (a.d + KC - 1) / KC;
+    const int n_it = static_cast<int>((a.Nb + TI - 1) / TI);
+    const int64_t Q = static_cast<int64_t>(n_it) * nch;
+
+    for (;;) {
+        if (tid == 0) *s_tile = static_cast<int>(atomicAdd(a.tile_counter, 1u));
+        if (tid < TU) {
+            st->tau_f[tid] = -INFINITY;
+            st->cnt[tid] = 0;
+            st->tau_key[tid] = 0ull;
+        }
+        __syncthreads();
+        const int ut = *s_tile;
+        if (ut >= a.n_row_tiles) break;
+        const int64_t u0 = static_cast<int64_t>(ut) * TU;
+        const int nu = (a.Ma - u0 < TU) ? static_cast<int>(a.Ma - u0) : TU;
+
+        if (warp == 0) {
+            if (A_RESIDENT) {
+                const uint32_t row_bytes = static_cast<uint32_t>(a.d) * 4u;
+                if (lane == 0) mbar_arrive_expect_tx(&bars[2], static_cast<uint32_t>(nu) * row_bytes);
+                __syncwarp();
+                for (int r = lane; r < nu; r += 32) bulk_g2s(sA_res + r * LDSF, a.A + (u0 + r) * a.d, row_bytes, &bars[2]);
+            }
+            issue_stage<A_RESIDENT>(a, stage0, &bars[0], u0, nu, 0, 0, lane);
+            if (Q > 1) issue_stage<A_RESIDENT>(a, stage1, &bars[1], u0, nu, static_cast<int>(1 / nch), static_cast<int>(1 % nch), lane);
+        }
+        if (A_RESIDENT) {
+            mbar_wait(&bars[2], phA);
+            phA ^= 1u;
+        }
+
+        float acc[8][8];
+        for (int64_t q = 0; q < Q; ++q) {
+            const int s = static_cast<int>(q & 1);
+            const int it = static_cast<int>(q / nch);
+            const int c = static_cast<int>(q % nch);
+            float *stage = s ? stage1 : stage0;
+            if (s) { mbar_wait(&bars[1], ph1); ph1 ^= 1u; } else { mbar_wait(&bars[0], ph0); ph0 ^= 1u; }
+
+            if (c == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+            }
+            const float *As = (A_RESIDENT ? sA_res : stage) + urow0 * LDSF;
+            const float *Bs = (A_RESIDENT ? stage : stage + kTileFloats) + icol0 * LDSF;
+            const int kc = (a.d - c * KC < KC) ? (a.d - c * KC) : KC;
+#pragma unroll 1
+            for (int kk = 0; kk < kc; kk += 4) {
+                float4 av[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) av[i] = *reinterpret_cast<const float4 *>(As + i * 4 * LDSF + kk);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bv = *reinterpret_cast<const float4 *>(Bs + j * 8 * LDSF + kk);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float t = acc[i][j];
+                        t = fmaf(av[i].x, bv.x, t);
+                        t = fmaf(av[i].y, bv.y, t);
+                        t = fmaf(av[i].z, bv.z, t);
+                        t = fmaf(av[i].w, bv.w, t);
+                        acc[i][j] = t;
+                    }
+                }
+            }
+
+            int flag = 0;
+            if (c == nch - 1) {
+                float tau[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) tau[i] = st->tau_f[urow0 + 4 * i];
+                bool any = false;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) any |= (acc[i][j] >= tau[i]);
+                if (any) {
+                    const int64_t i_base = static_cast<int64_t>(it) * TI + icol0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int ul = urow0 + 4 * i;
+                        if (ul < nu) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (acc[i][j] >= tau[i])
+                                    flag |= try_append(&s_args, st, cand_cta, ul, u0 + ul, i_base + 8 * j, acc[i][j]);
+                            }
+                        }
+                    }
+                }
+            }
+            const int need = __syncthreads_or(flag);  // stage s fully consumed; lists complete
+            if (need) {
+                uint64_t *scratch = reinterpret_cast<uint64_t *>(stage) + warp * kScratchKeys;
+                for (int r = 0; r < TU / kWarps; ++r) {
+                    const int ul = warp * (TU / kWarps) + r;
+                    if (st->cnt[ul] > kTrigger) merge_row(a, st, cand_cta, ul, scratch, lane);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+            }
+            if (warp == 0 && q + 2 < Q)
+                issue_stage<A_RESIDENT>(a, stage, s ? &bars[1] : &bars[0], u0, nu, static_cast<int>((q + 2) / nch),
+                                        static_cast<int>((q + 2) % nch), lane);
+        }
+
+        // every issued stage has been consumed: both stages are free -> sort scratch
+        {
+            uint64_t *scratch = reinterpret_cast<uint64_t *>(stage0) + warp * kScratchKeys;
+            for (int r = 0; r < TU / kWarps; ++r) {
+                const int ul = warp * (TU / kWarps) + r;
+                if (ul < nu) finish_row(a, st, cand_cta, ul, u0 + ul, scratch, lane);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    }
+}
+
+constexpr size_t smem_bytes(bool resident) {
+    return static_cast<size_t>(resident ? 3 : 4) * kTileBytes + sizeof(RowState) + 3 * sizeof(uint64_t) + 16;
+}
+
+int rank_grid(int64_t Ma, bool resident) {
+    const int64_t tiles = (Ma + TU - 1) / TU;
+    const int64_t slots = static_cast<int64_t>(sm_count()) * (resident ? 2 : 1);
+    return static_cast<int>(tiles < slots ? tiles : slots);
+}
+
+size_t rank_workspace_bytes(int64_t Ma, int d) {
+    const bool resident = d <= KC;
+    const int64_t slots = static_cast<int64_t>(sm_count()) * (resident ? 2 : 1);
+    return 256 + static_cast<size_t>(slots) * TU * CAP * sizeof(uint64_t);
+}
+
+int rank_launch(RankArgs a, void *workspace, size_t workspace_bytes, cudaStream_t stm) {
+    const bool resident = a.d <= KC;
+    if (workspace_bytes < rank_workspace_bytes(a.Ma, a.d)) return CHAOREC_E_WORKSPACE;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return CHAOREC_E_ALIGN;
+    a.tile_counter = reinterpret_cast<unsigned int *>(workspace);
+    a.cand = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(workspace) + 256);
+    const int64_t tiles = (a.Ma + TU - 1) / TU;
+    if (tiles > 0x7fffffffLL) return CHAOREC_E_UNSUPPORTED;
+    a.n_row_tiles = static_cast<int>(tiles);
+    if (cudaMemsetAsync(workspace, 0, 256, stm) != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
+    const int grid = rank_grid(a.Ma, resident);
+    const size_t smem = smem_bytes(resident);
+    cudaError_t e;
+    if (resident) {
+        e = cudaFuncSetAttribute(rank_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
+        rank_topk_kernel<true><<<grid, kThreads, smem, stm>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(rank_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
+        rank_topk_kernel<false><<<grid, kThreads, smem, stm>>>(a);
+    }
+    return launch_status();
+}
+
+// ---- canonical row norms: sequential fp64 sum of squares, one thread per row ----------------
+__global__ void row_norm_kernel(const float *__restrict__ x, int64_t N, int D, float *__restrict__ nrm) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float4 *row = reinterpret_cast<const float4 *>(x + i * D);
+    double ss = 0.0;
+    for (int q = 0; q < D / 4; ++q) {
+        const float4 v = row[q];
+        ss += static_cast<double>(v.x) * static_cast<double>(v.x);
+        ss += static_cast<double>(v.y) * static_cast<double>(v.y);
+        ss += static_cast<double>(v.z) * static_cast<double>(v.z);
+        ss += static_cast<double>(v.w) * static_cast<double>(v.w);
+    }
+    nrm[i] = static_cast<float>(sqrt(ss));
+}
+
+__global__ void row_scale_kernel(const float *__restrict__ x, const float *__restrict__ nrm, int64_t N, int D,
+                                 float *__restrict__ out) {
+    const int64_t total4 = N * (D / 4);
+    const int dq = D / 4;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total4;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float n = nrm[t / dq];
+        float4 v = reinterpret_cast<const float4 *>(x)[t];
+        v.x = v.x / n; v.y = v.y / n; v.z = v.z / n; v.w = v.w / n;
+        reinterpret_cast<float4 *>(out)[t] = v;
+    }
+}
+
+int normalize_launch(const float *x, int64_t N, int D, float *out, float *nrm, cudaStream_t stm) {
+    const int64_t b1 = (N + 63) / 64;
+    row_norm_kernel<<<static_cast<unsigned>(b1), 64, 0, stm>>>(x, N, D, nrm);
+    const int64_t total4 = N * (D / 4);
+    int64_t b2 = (total4 + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (b2 > cap) b2 = cap;
+    row_scale_kernel<<<static_cast<unsigned>(b2), 256, 0, stm>>>(x, nrm, N, D, out);
+    return launch_status();
+}
+
+size_t align256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
+
+}  // namespace
+}  // namespace chaorec
+
+using namespace chaorec;
+
+extern "C" size_t chaorec_score_mask_topk_workspace_bytes(int64_t U, int64_t I, int32_t d, int32_t K) {
+    (void)I; (void)K;
+    return rank_workspace_bytes(U, d);
+}
+
+extern "C" int chaorec_score_mask_topk_f32(const float *user_emb, const float *item_emb, const int64_t *mask_rowptr,
+                                           const int32_t *mask_col, float mask_value, int64_t U, int64_t I,
+                                           int32_t d, int32_t K, int64_t id_offset, int64_t *out_idx,
+                                           float *out_score, void *workspace, size_t workspace_bytes,
+                                           void *stream) {
+    if (!user_emb || !item_emb || !out_idx || U < 0 || I <= 0 || d <= 0) return CHAOREC_E_BADARG;
+    if (mask_rowptr && !mask_col) return CHAOREC_E_BADARG;
+    if (K < 1 || K > kMaxK || K > I || d % 4 != 0 || I > 0xFFFFFFF0LL) return CHAOREC_E_UNSUPPORTED;
+    if (!aligned16(user_emb) || !aligned16(item_emb)) return CHAOREC_E_ALIGN;
+    if (U == 0) return CHAOREC_OK;
+    RankArgs a{};
+    a.A = user_emb; a.B = item_emb; a.Ma = U; a.Nb = I; a.d = d; a.K = K;
+    a.mask_rowptr = mask_rowptr; a.mask_col = mask_col; a.mask_value = mask_value;
+    a.exclude_self = 0; a.self_off = 0; a.id_offset = id_offset;
+    a.out_idx = out_idx; a.out_score = out_score;
+    return rank_launch(a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int chaorec_l2_normalize_f32(const float *x, int64_t N, int32_t D, float *out, float *norms,
+                                        void *stream) {
+    if (!x || !out || !norms || N < 0 || D <= 0) return CHAOREC_E_BADARG;
+    if (D % 4 != 0) return CHAOREC_E_UNSUPPORTED;
+    if (!aligned16(x) || !aligned16(out)) return CHAOREC_E_ALIGN;
+    if (N == 0) return CHAOREC_OK;
+    return normalize_launch(x, N, D, out, norms, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t chaorec_knn_workspace_bytes(int64_t N, int32_t D, int32_t k) {
+    (void)k;
+    return align256(static_cast<size_t>(N) * D * sizeof(float)) + align256(static_cast<size_t>(N) * sizeof(float)) +
+           rank_workspace_bytes(N, D);
+}
+
+extern "C" int chaorec_knn_cosine_topk(const float *feats, int64_t N, int32_t D, int32_t k, int exclude_self,
+                                       int64_t row_lo, int64_t row_hi, float *out_val, int64_t *out_idx,
+                                       void *workspace, size_t workspace_bytes, void *stream) {
+    if (!feats || !out_val || !out_idx || N <= 0 || D <= 0 || row_lo < 0 || row_hi > N || row_lo > row_hi)
+        return CHAOREC_E_BADARG;
+    if (k < 1 || k > kMaxK || k > N - (exclude_self ? 1 : 0) || D % 4 != 0 || N > 0xFFFFFFF0LL)
+        return CHAOREC_E_UNSUPPORTED;
+    if (!aligned16(feats)) return CHAOREC_E_ALIGN;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return CHAOREC_E_ALIGN;
+    if (workspace_bytes < chaorec_knn_workspace_bytes(N, D, k)) return CHAOREC_E_WORKSPACE;
+    if (row_lo == row_hi) return CHAOREC_OK;
+    cudaStream_t stm = static_cast<cudaStream_t>(stream);
+    unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+    float *cn = reinterpret_cast<float *>(ws);
+    ws += align256(static_cast<size_t>(N) * D * sizeof(float));
+    float *nrm = reinterpret_cast<float *>(ws);
+    ws += align256(static_cast<size_t>(N) * sizeof(float));
+    int rc = normalize_launch(feats, N, D, cn, nrm, stm);
+    if (rc != CHAOREC_OK) return rc;
+    RankArgs a{};
+    a.A = cn + row_lo * D; a.B = cn; a.Ma = row_hi - row_lo; a.Nb = N; a.d = D; a.K = k;
+    a.mask_rowptr = nullptr; a.mask_col = nullptr; a.mask_value = 0.0f;
+    a.exclude_self = exclude_self ? 1 : 0; a.self_off = row_lo; a.id_offset = 0;
+    a.out_idx = out_idx; a.out_score = out_val;
+    return rank_launch(a, ws, workspace_bytes - static_cast<size_t>(ws - reinterpret_cast<unsigned char *>(workspace)),
+                       stm);
+}

@@ -1,0 +1,302 @@
+// K1: CSR SpMM with fused degree scaling and layer-mean accumulation (fp32).
+//
+// Replaces torch.sparse.mm(adj, x) (Model/FREEDOM.py:168,174) and the PyG gather/scatter-add
+// of LightGCNConv (Model/LightGCN.py:28-46).  HBM-bound gather of 4*d-byte embedding rows:
+//   * a sub-warp of LANES lanes owns one destination row; each lane carries NV float4
+//     accumulators, so one 64-d row is one fully coalesced 256-byte request of 16 lanes
+//     (two destination rows per warp);
+//   * column indices / edge weights are read coalesced once per LANES edges and broadcast with
+//     warp shuffles; the gathers are issued four at a time before the FMAs that consume them;
+//   * effective edge weight row_scale[r] * val[e] * col_scale[c] is formed in registers, so
+//     D^-1/2 A D^-1/2 never exists as an edge-value array (V1-V5 of SURVEY.md §2.3 are all
+//     expressible);
+//   * the epilogue writes y and/or folds alpha*y into the running layer mean;
+//   * hub rows (Zipf item rows with 10^3..10^6 neighbours) are cut into fixed chunks, each
+//     reduced by a whole CTA through shared memory into a partial row, then summed in chunk
+//     order -> deterministic, no atomics, no serial tail.
+#include "common.cuh"
+
+namespace chaorec {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kHubThreshold = 1024;
+constexpr int kHubChunk = 4096;
+
+struct SpmmArgs {
+    const int64_t *rowptr;
+    const int32_t *col;
+    const float *val;
+    const float *row_scale;
+    const float *col_scale;
+    const float4 *x;
+    float4 *y;
+    float4 *acc;
+    float alpha;
+    int acc_mode;
+    const int32_t *hub_rows;
+    const int64_t *hub_chunk_ptr;
+    int n_hub;
+    float4 *hub_partials;
+    int64_t M;
+    int dq;  // d / 4
+};
+
+template <int LANES>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+    constexpr unsigned kOnes = (LANES >= 32) ? 0xffffffffu : ((1u << (LANES & 31)) - 1u);
+    return (LANES >= 32) ? kOnes : (kOnes << ((lane / LANES) * LANES));
+}
+
+// Accumulate edges [e_lo, e_hi) of one row into acc[NV]; all LANES lanes of the group call it
+// with identical bounds.
+template <int LANES, int NV>
+__device__ __forceinline__ void gather_edges(const SpmmArgs &a, int64_t e_lo, int64_t e_hi, int gl, unsigned mask,
+                                             float4 (&acc)[NV]) {
+    for (int64_t e0 = e_lo; e0 < e_hi; e0 += LANES) {
+        const int64_t e = e0 + gl;
+        int c = 0;
+        float w = 0.0f;
+        if (e < e_hi) {
+            c = __ldg(a.col + e);
+            w = a.val ? __ldg(a.val + e) : 1.0f;
+            if (a.col_scale) w *= __ldg(a.col_scale + c);
+        }
+        const int cnt = (e_hi - e0 < LANES) ? static_cast<int>(e_hi - e0) : LANES;
+        int j = 0;
+        for (; j + 4 <= cnt; j += 4) {
+            int cj[4];
+            float wj[4];
+            float4 xv[4][NV];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                cj[t] = __shfl_sync(mask, c, j + t, LANES);
+                wj[t] = __shfl_sync(mask, w, j + t, LANES);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float4 *xr = a.x + static_cast<int64_t>(cj[t]) * a.dq;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const int q = gl + v * LANES;
+                    xv[t][v] = (q < a.dq) ? __ldg(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    acc[v].x = fmaf(wj[t], xv[t][v].x, acc[v].x);
+                    acc[v].y = fmaf(wj[t], xv[t][v].y, acc[v].y);
+                    acc[v].z = fmaf(wj[t], xv[t][v].z, acc[v].z);
+                    acc[v].w = fmaf(wj[t], xv[t][v].w, acc[v].w);
+                }
+            }
+        }
+        for (; j < cnt; ++j) {
+            const int cj = __shfl_sync(mask, c, j, LANES);
+            const float wj = __shfl_sync(mask, w, j, LANES);
+            const float4 *xr = a.x + static_cast<int64_t>(cj) * a.dq;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int q = gl + v * LANES;
+                if (q < a.dq) {
+                    const float4 xv = __ldg(xr + q);
+                    acc[v].x = fmaf(wj, xv.x, acc[v].x);
+                    acc[v].y = fmaf(wj, xv.y, acc[v].y);
+                    acc[v].z = fmaf(wj, xv.z, acc[v].z);
+                    acc[v].w = fmaf(wj, xv.w, acc[v].w);
+                }
+            }
+        }
+    }
+}
+
+// y = row_scale * acc; optional store; optional layer-mean update.
+template <int LANES, int NV>
+__device__ __forceinline__ void row_epilogue(const SpmmArgs &a, int64_t r, int gl, float4 (&acc)[NV]) {
+    const float rs = a.row_scale ? __ldg(a.row_scale + r) : 1.0f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const int q = gl + v * LANES;
+        if (q >= a.dq) continue;
+        float4 yv = acc[v];
+        if (a.row_scale) {
+            yv.x *= rs; yv.y *= rs; yv.z *= rs; yv.w *= rs;
+        }
+        const int64_t o = r * a.dq + q;
+        if (a.y) a.y[o] = yv;
+        if (a.acc) {
+            float4 base;
+            if (a.acc_mode == 1) {
+                const float4 x0 = __ldg(a.x + o);
+                base = make_float4(a.alpha * x0.x, a.alpha * x0.y, a.alpha * x0.z, a.alpha * x0.w);
+            } else {
+                base = a.acc[o];
+            }
+            base.x = fmaf(a.alpha, yv.x, base.x);
+            base.y = fmaf(a.alpha, yv.y, base.y);
+            base.z = fmaf(a.alpha, yv.z, base.z);
+            base.w = fmaf(a.alpha, yv.w, base.w);
+            a.acc[o] = base;
+        }
+    }
+}
+
+template <int LANES, int NV>
+__global__ void __launch_bounds__(kThreads) spmm_rows_kernel(const SpmmArgs a) {
+    constexpr int kGroups = kThreads / LANES;
+    const int lane = threadIdx.x & 31;
+    const int gl = threadIdx.x % LANES;
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * kGroups + threadIdx.x / LANES;
+    if (r >= a.M) return;
+    const unsigned mask = group_mask<LANES>(lane);
+    const int64_t e_lo = __ldg(a.rowptr + r), e_hi = __ldg(a.rowptr + r + 1);
+    if (a.hub_rows != nullptr && e_hi - e_lo > kHubThreshold) return;  // taken by the hub kernels
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_edges<LANES, NV>(a, e_lo, e_hi, gl, mask, acc);
+    row_epilogue<LANES, NV>(a, r, gl, acc);
+}
+
+// One CTA per (hub row, chunk): every sub-warp reduces a contiguous slice of the chunk, the
+// slices are summed in slice order through shared memory and stored as one partial row.
+template <int LANES, int NV>
+__global__ void __launch_bounds__(kThreads) spmm_hub_chunk_kernel(const SpmmArgs a) {
+    constexpr int kGroups = kThreads / LANES;
+    __shared__ float4 part[kGroups][LANES * NV];
+    const int lane = threadIdx.x & 31;
+    const int gl = threadIdx.x % LANES;
+    const int g = threadIdx.x / LANES;
+    const int64_t chunk = blockIdx.x;
+    // hub row h with hub_chunk_ptr[h] <= chunk < hub_chunk_ptr[h+1]
+    int lo = 0, hi = a.n_hub;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(a.hub_chunk_ptr + mid) <= chunk) lo = mid; else hi = mid;
+    }
+    const int64_t r = __ldg(a.hub_rows + lo);
+    const int64_t c_in_row = chunk - __ldg(a.hub_chunk_ptr + lo);
+    const int64_t row_lo = __ldg(a.rowptr + r), row_hi = __ldg(a.rowptr + r + 1);
+    const int64_t c_lo = row_lo + c_in_row * kHubChunk;
+    const int64_t c_hi = (c_lo + kHubChunk < row_hi) ? c_lo + kHubChunk : row_hi;
+    constexpr int kSlice = kHubChunk / kGroups;
+    int64_t e_lo = c_lo + static_cast<int64_t>(g) * kSlice;
+    int64_t e_hi = e_lo + kSlice;
+    if (e_lo > c_hi) e_lo = c_hi;
+    if (e_hi > c_hi) e_hi = c_hi;
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_edges<LANES, NV>(a, e_lo, e_hi, gl, group_mask<LANES>(lane), acc);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) part[g][gl + v * LANES] = acc[v];
+    __syncthreads();
+    for (int q = threadIdx.x; q < a.dq; q += kThreads) {
+        const int slot = q;  // q = gl + v*LANES by construction of the layout above
+        float4 s = part[0][slot];
+        for (int gg = 1; gg < kGroups; ++gg) {
+            const float4 p = part[gg][slot];
+            s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+        }
+        a.hub_partials[chunk * a.dq + q] = s;
+    }
+}
+
+template <int LANES, int NV>
+__global__ void __launch_bounds__(kThreads) spmm_hub_finish_kernel(const SpmmArgs a) {
+    constexpr int kGroups = kThreads / LANES;
+    const int gl = threadIdx.x % LANES;
+    const int h = blockIdx.x * kGroups + threadIdx.x / LANES;
+    if (h >= a.n_hub) return;
+    const int64_t r = __ldg(a.hub_rows + h);
+    const int64_t c_lo = __ldg(a.hub_chunk_ptr + h), c_hi = __ldg(a.hub_chunk_ptr + h + 1);
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t c = c_lo; c < c_hi; ++c) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int q = gl + v * LANES;
+            if (q < a.dq) {
+                const float4 p = a.hub_partials[c * a.dq + q];
+                acc[v].x += p.x; acc[v].y += p.y; acc[v].z += p.z; acc[v].w += p.w;
+            }
+        }
+    }
+    row_epilogue<LANES, NV>(a, r, gl, acc);
+}
+
+template <int LANES, int NV>
+int launch_spmm(const SpmmArgs &a, int64_t n_hub_chunks, cudaStream_t st) {
+    constexpr int kGroups = kThreads / LANES;
+    const int64_t blocks = (a.M + kGroups - 1) / kGroups;
+    if (blocks > 0x7fffffffLL) return CHAOREC_E_UNSUPPORTED;
+    if (blocks > 0) spmm_rows_kernel<LANES, NV><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(a);
+    if (a.hub_rows != nullptr && a.n_hub > 0 && n_hub_chunks > 0) {
+        if (n_hub_chunks > 0x7fffffffLL) return CHAOREC_E_UNSUPPORTED;
+        spmm_hub_chunk_kernel<LANES, NV><<<static_cast<unsigned>(n_hub_chunks), kThreads, 0, st>>>(a);
+        spmm_hub_finish_kernel<LANES, NV><<<(a.n_hub + kGroups - 1) / kGroups, kThreads, 0, st>>>(a);
+    }
+    return launch_status();
+}
+
+__global__ void degree_inv_sqrt_kernel(const int64_t *__restrict__ rowptr, int64_t M, float eps,
+                                       float *__restrict__ out) {
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    const float deg = static_cast<float>(rowptr[r + 1] - rowptr[r]) + eps;
+    out[r] = 1.0f / sqrtf(deg);  // IEEE sqrt + division; 0 -> +inf like deg.pow(-0.5)
+}
+
+}  // namespace
+}  // namespace chaorec
+
+using namespace chaorec;
+
+extern "C" int32_t chaorec_spmm_hub_threshold(void) { return kHubThreshold; }
+extern "C" int32_t chaorec_spmm_hub_chunk(void) { return kHubChunk; }
+
+extern "C" int chaorec_degree_inv_sqrt(const int64_t *rowptr, int64_t M, float eps, float *out, void *stream) {
+    if (!rowptr || !out || M < 0) return CHAOREC_E_BADARG;
+    if (M == 0) return CHAOREC_OK;
+    const int64_t blocks = (M + 255) / 256;
+    degree_inv_sqrt_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(rowptr, M,
+                                                                                                         eps, out);
+    return launch_status();
+}
+
+extern "C" int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float *val,
+                                    const float *row_scale, const float *col_scale, const float *x, float *y,
+                                    float *acc, float alpha, int32_t acc_mode, const int32_t *hub_rows,
+                                    const int64_t *hub_chunk_ptr, int32_t n_hub, int64_t n_hub_chunks,
+                                    float *hub_partials, int64_t M, int64_t N, int32_t d, void *stream) {
+    if (!rowptr || !x || M < 0 || N < 0 || d <= 0) return CHAOREC_E_BADARG;
+    if (!y && !acc) return CHAOREC_E_BADARG;
+    if (acc_mode != 0 && acc_mode != 1) return CHAOREC_E_BADARG;
+    if (acc && acc_mode == 1 && M != N) return CHAOREC_E_BADARG;
+    if (d % 4 != 0 || d > 512) return CHAOREC_E_UNSUPPORTED;
+    if (!aligned16(x) || (y && !aligned16(y)) || (acc && !aligned16(acc))) return CHAOREC_E_ALIGN;
+    if (hub_rows && n_hub > 0 && (!hub_chunk_ptr || !hub_partials || !aligned16(hub_partials)))
+        return CHAOREC_E_BADARG;
+    if (M == 0) return CHAOREC_OK;
+    if (!col) return CHAOREC_E_BADARG;
+    SpmmArgs a;
+    a.rowptr = rowptr; a.col = col; a.val = val; a.row_scale = row_scale; a.col_scale = col_scale;
+    a.x = reinterpret_cast<const float4 *>(x);
+    a.y = reinterpret_cast<float4 *>(y);
+    a.acc = reinterpret_cast<float4 *>(acc);
+    a.alpha = alpha; a.acc_mode = acc_mode;
+    a.hub_rows = (hub_rows && n_hub > 0) ? hub_rows : nullptr;
+    a.hub_chunk_ptr = hub_chunk_ptr; a.n_hub = a.hub_rows ? n_hub : 0;
+    a.hub_partials = reinterpret_cast<float4 *>(hub_partials);
+    a.M = M; a.dq = d / 4;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d == 32) return launch_spmm<8, 1>(a, n_hub_chunks, st);
+    if (d == 64) return launch_spmm<16, 1>(a, n_hub_chunks, st);
+    if (d <= 128) return launch_spmm<32, 1>(a, n_hub_chunks, st);
+    if (d <= 256) return launch_spmm<32, 2>(a, n_hub_chunks, st);
+    if (d <= 384) return launch_spmm<32, 3>(a, n_hub_chunks, st);
+    return launch_spmm<32, 4>(a, n_hub_chunks, st);
+}

@@ -1,0 +1,288 @@
+"""Normalized-adjacency propagation: drop-ins for the reference's SpMM seam.
+
+Reference call sites replaced (paths relative to the ChaoRec checkout):
+  * ``torch.sparse.mm(adj, x)``                     Model/FREEDOM.py:168,174 (+35 models)
+  * ``LightGCNConv(...)(x, edge_index)``            Model/LightGCN.py:21-46, Model/LATTICE.py:18-42
+  * the L-layer chain + layer mean                  Model/LightGCN.py:76-95, Model/FREEDOM.py:171-178
+
+Host logic only; all arithmetic runs in csrc/spmm.cu through the C ABI.
+"""
+from __future__ import annotations
+
+import weakref
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class CSRGraph:
+    """A (M x N) sparse matrix in CSR on one GPU + the hub-row plan the SpMM kernel wants."""
+    rowptr: torch.Tensor              # int64 [M+1]
+    col: torch.Tensor                 # int32 [nnz]
+    val: Optional[torch.Tensor]       # float32 [nnz] or None (=> ones)
+    M: int
+    N: int
+    row_scale: Optional[torch.Tensor] = None   # float32 [M]
+    col_scale: Optional[torch.Tensor] = None   # float32 [N]
+    hub_rows: Optional[torch.Tensor] = None    # int32 [n_hub]
+    hub_chunk_ptr: Optional[torch.Tensor] = None  # int64 [n_hub+1]
+    n_hub: int = 0
+    n_hub_chunks: int = 0
+    _partials: Dict[int, torch.Tensor] = field(default_factory=dict)
+    _transposed: Optional["CSRGraph"] = None
+    symmetric: bool = False
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col.numel())
+
+    @property
+    def device(self) -> torch.device:
+        return self.rowptr.device
+
+    def plan_hubs(self) -> "CSRGraph":
+        lib = _lib.load()
+        thr, chunk = lib.chaorec_spmm_hub_threshold(), lib.chaorec_spmm_hub_chunk()
+        deg = self.rowptr[1:] - self.rowptr[:-1]
+        hubs = torch.nonzero(deg > thr).flatten()
+        self.n_hub = int(hubs.numel())
+        if self.n_hub:
+            chunks = (deg[hubs] + (chunk - 1)) // chunk
+            ptr = torch.zeros(self.n_hub + 1, dtype=torch.int64, device=self.device)
+            ptr[1:] = torch.cumsum(chunks, 0)
+            self.hub_rows = hubs.to(torch.int32).contiguous()
+            self.hub_chunk_ptr = ptr
+            self.n_hub_chunks = int(ptr[-1].item())
+        else:
+            self.hub_rows, self.hub_chunk_ptr, self.n_hub_chunks = None, None, 0
+        self._partials.clear()
+        return self
+
+    def partials(self, d: int) -> Optional[torch.Tensor]:
+        if not self.n_hub:
+            return None
+        buf = self._partials.get(d)
+        if buf is None:
+            buf = torch.empty(self.n_hub_chunks * d, dtype=torch.float32, device=self.device)
+            self._partials[d] = buf
+        return buf
+
+    def transposed(self) -> "CSRGraph":
+        """CSR of A^T (for the backward of spmm); symmetric graphs reuse themselves."""
+        if self.symmetric:
+            return self
+        if self._transposed is None:
+            rows = torch.repeat_interleave(torch.arange(self.M, device=self.device, dtype=torch.int64),
+                                           self.rowptr[1:] - self.rowptr[:-1])
+            t = csr_from_coo(self.col.to(torch.int64), rows, self.val, self.N, self.M)
+            t.row_scale, t.col_scale = self.col_scale, self.row_scale
+            t._transposed = self
+            self._transposed = t
+        return self._transposed
+
+
+def csr_from_coo(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], M: int, N: int) -> CSRGraph:
+    """COO (int64 row/col as stored by torch.sparse_coo_tensor, duplicates allowed) -> CSRGraph."""
+    _lib.require_cuda(row, "row")
+    lib = _lib.load()
+    dev = row.device
+    row = row.to(torch.int64).contiguous()
+    col = col.to(torch.int64).contiguous()
+    nnz = int(row.numel())
+    if val is not None:
+        val = val.to(torch.float32).contiguous()
+    rowptr = torch.empty(M + 1, dtype=torch.int64, device=dev)
+    out_col = torch.empty(nnz, dtype=torch.int32, device=dev)
+    out_val = torch.empty(nnz, dtype=torch.float32, device=dev) if val is not None else None
+    ws = _lib.workspace(lib.chaorec_coo_to_csr_workspace_bytes(nnz, M), dev)
+    with torch.cuda.device(dev):
+        rc = lib.chaorec_coo_to_csr(_lib.ptr(row), _lib.ptr(col), _lib.ptr(val), nnz, M, N, _lib.ptr(rowptr),
+                                    _lib.ptr(out_col), _lib.ptr(out_val), _lib.ptr(ws), ws.numel(),
+                                    _lib.stream_ptr(dev))
+    _lib.check(rc, "chaorec_coo_to_csr")
+    return CSRGraph(rowptr, out_col, out_val, M, N).plan_hubs()
+
+
+_coo_cache: Dict[int, Tuple[weakref.ref, int, int, CSRGraph]] = {}
+
+
+def csr_from_sparse_coo(adj: torch.Tensor) -> CSRGraph:
+    """Cached conversion of a torch sparse COO tensor (keyed on identity + storage of its values:
+    FREEDOM replaces ``masked_adj`` by a new tensor every epoch, Model/FREEDOM.py:143-162)."""
+    if isinstance(adj, CSRGraph):
+        return adj
+    if adj.layout != torch.sparse_coo:
+        raise TypeError("expected a torch.sparse_coo tensor or a CSRGraph")
+    idx = adj._indices()
+    vals = adj._values()
+    key = id(adj)
+    hit = _coo_cache.get(key)
+    if hit is not None and hit[0]() is adj and hit[1] == vals.data_ptr() and hit[2] == vals._version:
+        return hit[3]
+    g = csr_from_coo(idx[0], idx[1], vals, adj.shape[0], adj.shape[1])
+    if len(_coo_cache) > 64:
+        for k in [k for k, v in _coo_cache.items() if v[0]() is None]:
+            _coo_cache.pop(k, None)
+    _coo_cache[key] = (weakref.ref(adj), vals.data_ptr(), vals._version, g)
+    return g
+
+
+def _spmm_raw(g: CSRGraph, x: torch.Tensor, y: Optional[torch.Tensor], acc: Optional[torch.Tensor], alpha: float,
+              acc_mode: int) -> None:
+    lib = _lib.load()
+    d = x.shape[1]
+    with torch.cuda.device(x.device):
+        rc = lib.chaorec_spmm_csr_f32(
+            _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.val), _lib.ptr(g.row_scale), _lib.ptr(g.col_scale),
+            _lib.ptr(x), _lib.ptr(y), _lib.ptr(acc), float(alpha), int(acc_mode), _lib.ptr(g.hub_rows),
+            _lib.ptr(g.hub_chunk_ptr), g.n_hub, g.n_hub_chunks, _lib.ptr(g.partials(d)), g.M, g.N, d,
+            _lib.stream_ptr(x.device))
+    _lib.check(rc, "chaorec_spmm_csr_f32")
+
+
+def _check_x(g: CSRGraph, x: torch.Tensor) -> torch.Tensor:
+    _lib.require_cuda(x, "x")
+    if x.dim() != 2 or x.shape[0] != g.N:
+        raise RuntimeError(f"spmm: x must be [{g.N}, d], got {tuple(x.shape)}")
+    if x.dtype != torch.float32:
+        raise RuntimeError("spmm: x must be float32")
+    return x.contiguous()
+
+
+class _SpmmFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, g: CSRGraph):
+        x = _check_x(g, x)
+        y = torch.empty(g.M, x.shape[1], dtype=torch.float32, device=x.device)
+        _spmm_raw(g, x, y, None, 0.0, 0)
+        ctx.g = g
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gt = ctx.g.transposed()
+        gy = gy.contiguous()
+        gx = torch.empty(gt.M, gy.shape[1], dtype=torch.float32, device=gy.device)
+        _spmm_raw(gt, gy, gx, None, 0.0, 0)
+        return gx, None
+
+
+def spmm(adj, x: torch.Tensor) -> torch.Tensor:
+    """Drop-in for ``torch.sparse.mm(adj, x)`` (fp32, differentiable in ``x``)."""
+    return _SpmmFn.apply(x, csr_from_sparse_coo(adj))
+
+
+class _PropagateMeanFn(torch.autograd.Function):
+    """out = sum_l w_l A^l x0 with the layer mean folded into each SpMM's epilogue."""
+
+    @staticmethod
+    def forward(ctx, x0, g: CSRGraph, n_layers: int, alpha: float, include_layer0: bool):
+        x0 = _check_x(g, x0)
+        ctx.g, ctx.n_layers, ctx.alpha, ctx.include0 = g, n_layers, alpha, include_layer0
+        return _propagate_mean_raw(g, x0, n_layers, alpha, include_layer0)
+
+    @staticmethod
+    def backward(ctx, gout):
+        gx = _propagate_mean_raw(ctx.g.transposed(), gout.contiguous(), ctx.n_layers, ctx.alpha, ctx.include0)
+        return gx, None, None, None, None
+
+
+def _propagate_mean_raw(g: CSRGraph, x0: torch.Tensor, n_layers: int, alpha: float, include0: bool) -> torch.Tensor:
+    if g.M != g.N:
+        raise RuntimeError("propagate_mean needs a square adjacency")
+    if n_layers == 0:
+        return x0 * alpha if include0 else torch.zeros_like(x0)
+    acc = torch.empty_like(x0)
+    bufs = [torch.empty_like(x0), torch.empty_like(x0)] if n_layers > 1 else [None, None]
+    cur = x0
+    for l in range(n_layers):
+        last = l == n_layers - 1
+        y = None if last else bufs[l & 1]
+        if l == 0:
+            if include0:
+                _spmm_raw(g, cur, y, acc, alpha, 1)       # acc = alpha*x0 + alpha*y
+            else:
+                acc.zero_()
+                _spmm_raw(g, cur, y, acc, alpha, 0)
+        else:
+            _spmm_raw(g, cur, y, acc, alpha, 0)           # acc += alpha*y
+        cur = y
+    return acc
+
+
+def propagate_mean(adj, x0: torch.Tensor, n_layers: int, include_layer0: bool = True,
+                   alpha: Optional[float] = None) -> torch.Tensor:
+    """Fused ``n_layers`` propagation + layer combination.
+
+    ``include_layer0=True``  -> mean over layers 0..L  (Model/LightGCN.py:86-93, Model/FREEDOM.py:177-178)
+    ``include_layer0=False`` -> mean over layers 1..L  (Model/SimGCL.py:112-120)
+    ``adj`` is a torch sparse COO tensor, a ``CSRGraph`` or an ``edge_index`` handled by
+    ``graph_from_edge_index``.
+    """
+    if (isinstance(adj, torch.Tensor) and adj.layout == torch.strided and adj.dim() == 2 and adj.shape[0] == 2
+            and not adj.is_floating_point()):
+        g = graph_from_edge_index(adj, x0.size(0))
+    else:
+        g = csr_from_sparse_coo(adj)
+    if alpha is None:
+        alpha = 1.0 / (n_layers + 1 if include_layer0 else max(n_layers, 1))
+    return _PropagateMeanFn.apply(x0, g, int(n_layers), float(alpha), bool(include_layer0))
+
+
+_edge_cache: Dict[Tuple[int, int, int], Tuple[weakref.ref, CSRGraph]] = {}
+
+
+def graph_from_edge_index(edge_index: torch.Tensor, num_nodes: int) -> CSRGraph:
+    """PyG ``LightGCNConv`` graph (Model/LightGCN.py:28-40): out[col] += deg^-1/2[row]*deg^-1/2[col]*x[row]
+    with deg = degree(row).  CSR rows are destinations (``edge_index[1]``), columns sources."""
+    key = (id(edge_index), edge_index.data_ptr(), num_nodes)
+    hit = _edge_cache.get(key)
+    if hit is not None and hit[0]() is edge_index:
+        return hit[1]
+    _lib.require_cuda(edge_index, "edge_index")
+    lib = _lib.load()
+    ei = edge_index.long()
+    src, dst = ei[0], ei[1]
+    g = csr_from_coo(dst, src, None, num_nodes, num_nodes)
+    # degree(row) counts a node as a *source*; the symmetrised list (Model/LightGCN.py:63-64)
+    # makes that equal to the CSR row length, which the kernel-side helper reads off rowptr.
+    src_deg = torch.bincount(src, minlength=num_nodes)
+    row_len = g.rowptr[1:] - g.rowptr[:-1]
+    dis = torch.empty(num_nodes, dtype=torch.float32, device=ei.device)
+    if torch.equal(src_deg, row_len):
+        with torch.cuda.device(ei.device):
+            _lib.check(lib.chaorec_degree_inv_sqrt(_lib.ptr(g.rowptr), num_nodes, 0.0, _lib.ptr(dis),
+                                                   _lib.stream_ptr(ei.device)), "chaorec_degree_inv_sqrt")
+        g.symmetric = bool(torch.equal(torch.sort(src * num_nodes + dst)[0], torch.sort(dst * num_nodes + src)[0]))
+    else:
+        dis = src_deg.to(torch.float32).pow(-0.5)
+    g.row_scale, g.col_scale = dis, dis
+    if len(_edge_cache) > 16:
+        for k in [k for k, v in _edge_cache.items() if v[0]() is None]:
+            _edge_cache.pop(k, None)
+    _edge_cache[key] = (weakref.ref(edge_index), g)
+    return g
+
+
+class LightGCNConv(torch.nn.Module):
+    """Same constructor and call signature as Model/LightGCN.py:21-46 (no learnable state)."""
+
+    def __init__(self, in_channels, out_channels, aggr='add', **kwargs):
+        super().__init__()
+        self.aggr = aggr
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+
+    def forward(self, x, edge_index):
+        return _SpmmFn.apply(x, graph_from_edge_index(edge_index, x.size(0)))
+
+
+def lightgcn_forward(user_weight: torch.Tensor, item_weight: torch.Tensor, edge_index: torch.Tensor,
+                     n_layers: int) -> torch.Tensor:
+    """Fused body of ``LightGCN.forward`` (Model/LightGCN.py:76-95)."""
+    x0 = torch.cat((user_weight, item_weight), dim=0)
+    return propagate_mean(graph_from_edge_index(edge_index, x0.size(0)), x0, n_layers, True)

@@ -1,0 +1,215 @@
+"""Full-ranking evaluation: drop-ins for ``gene_ranklist`` and ``evaluate``.
+
+Reference call sites replaced (paths relative to the ChaoRec checkout):
+  * ``model.gene_ranklist(topk=50)``            Model/LightGCN.py:137-162 (identical in 16 models;
+                                                 batched form Model/MMGCN.py:204-244)
+  * ``evaluate(model, data, ranklist, topk)``   train_and_evaluate.py:516-520 -> utils.gene_metrics
+                                                 (utils.py:112-139) -> metrics.py:13-57
+
+Host logic only: data-format conversion (python dict / object arrays -> CSR) and the calls into
+csrc/rank_topk.cu and csrc/hits_metrics.cu through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from dataclasses import dataclass
+from typing import Dict, Iterable, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+METRIC_NAMES = ('precision', 'recall', 'ndcg', 'hit_rate', 'map')
+
+
+@dataclass
+class MaskCSR:
+    """Per-user train items as LOCAL item ids, sorted ascending and unique inside each row."""
+    rowptr: torch.Tensor  # int64 [U+1]
+    col: torch.Tensor     # int32 [nnz]
+
+
+def build_mask_csr(user_item_dict: Dict[int, Iterable[int]], num_user: int, num_item: int,
+                   device: torch.device) -> MaskCSR:
+    """``user_item_dict`` {user: [global item ids]} (train items only, dataload.py:30) -> MaskCSR.
+    Items outside [num_user, num_user+num_item) are dropped (they cannot index the score matrix)."""
+    users, items = [], []
+    for u, its in user_item_dict.items():
+        u = int(u)
+        if 0 <= u < num_user:
+            arr = np.asarray(list(its), dtype=np.int64) - num_user
+            users.append(np.full(arr.shape, u, dtype=np.int64))
+            items.append(arr)
+    if users:
+        uu = np.concatenate(users)
+        ii = np.concatenate(items)
+        ok = (ii >= 0) & (ii < num_item)
+        keys = np.unique(uu[ok] * num_item + ii[ok])
+        uu, ii = keys // num_item, keys % num_item
+    else:
+        uu = np.zeros(0, dtype=np.int64)
+        ii = np.zeros(0, dtype=np.int64)
+    rowptr = np.zeros(num_user + 1, dtype=np.int64)
+    np.cumsum(np.bincount(uu, minlength=num_user), out=rowptr[1:])
+    return MaskCSR(torch.from_numpy(rowptr).to(device), torch.from_numpy(ii.astype(np.int32)).to(device))
+
+
+def mask_csr_from_edges(users: torch.Tensor, local_items: torch.Tensor, num_user: int, num_item: int) -> MaskCSR:
+    """Same as ``build_mask_csr`` from device tensors of (user, local item) pairs."""
+    keys = torch.unique(users.to(torch.int64) * num_item + local_items.to(torch.int64))
+    uu = keys // num_item
+    rowptr = torch.zeros(num_user + 1, dtype=torch.int64, device=keys.device)
+    rowptr[1:] = torch.cumsum(torch.bincount(uu, minlength=num_user), 0)
+    return MaskCSR(rowptr, (keys % num_item).to(torch.int32).contiguous())
+
+
+def rank_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, mask: Optional[MaskCSR], topk: int,
+              mask_value: float = 1e-6, id_offset: int = 0, return_scores: bool = False):
+    """Fused score -> mask -> top-K.  Returns int64 [U, topk] (and float32 scores)."""
+    _lib.require_cuda(user_emb, "user_emb")
+    _lib.require_cuda(item_emb, "item_emb")
+    lib = _lib.load()
+    dev = user_emb.device
+    user_emb = user_emb.detach().to(torch.float32).contiguous()
+    item_emb = item_emb.detach().to(torch.float32).contiguous()
+    U, d = user_emb.shape
+    I = item_emb.shape[0]
+    if item_emb.shape[1] != d:
+        raise RuntimeError("user and item embeddings must have the same width")
+    out_idx = torch.empty(U, topk, dtype=torch.int64, device=dev)
+    out_score = torch.empty(U, topk, dtype=torch.float32, device=dev) if return_scores else None
+    ws = _lib.workspace(lib.chaorec_score_mask_topk_workspace_bytes(U, I, d, topk), dev)
+    with torch.cuda.device(dev):
+        rc = lib.chaorec_score_mask_topk_f32(
+            _lib.ptr(user_emb), _lib.ptr(item_emb), _lib.ptr(mask.rowptr) if mask else None,
+            _lib.ptr(mask.col) if mask else None, float(np.float32(mask_value)), U, I, d, int(topk),
+            int(id_offset), _lib.ptr(out_idx), _lib.ptr(out_score), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(rc, "chaorec_score_mask_topk_f32")
+    return (out_idx, out_score) if return_scores else out_idx
+
+
+_mask_cache: Dict[int, Tuple[weakref.ref, int, MaskCSR]] = {}
+
+
+def _model_mask(model, device) -> MaskCSR:
+    d = model.user_item_dict
+    key = id(d)
+    hit = _mask_cache.get(key)
+    if hit is not None and hit[1] == len(d) and hit[2].rowptr.device == device:
+        return hit[2]
+    m = build_mask_csr(d, model.num_user, model.num_item, device)
+    _mask_cache[key] = (None, len(d), m)
+    return m
+
+
+def gene_ranklist(model, topk: int = 50, mask_value: float = 1e-6, device: Optional[torch.device] = None,
+                  to_cpu: bool = True) -> torch.Tensor:
+    """Drop-in for ``model.gene_ranklist(topk)`` (Model/LightGCN.py:137-162).
+
+    Uses ``model.result`` (the cached embeddings of the last forward), ``model.num_user``,
+    ``model.num_item`` and ``model.user_item_dict`` exactly like the reference method, and returns
+    a LongTensor [num_user, topk] of GLOBAL item ids (on the CPU like the reference unless
+    ``to_cpu=False``).  Bind it as a method with ``types.MethodType(gene_ranklist, model)``.
+    """
+    result = model.result
+    if device is None:
+        device = result.device if result.is_cuda else torch.device('cuda', torch.cuda.current_device())
+    result = result.detach().to(device)
+    U, I = model.num_user, model.num_item
+    out = rank_topk(result[:U], result[U:U + I], _model_mask(model, device), topk, mask_value, id_offset=U)
+    return out.cpu() if to_cpu else out
+
+
+@dataclass
+class PositivesCSR:
+    """``val_data`` / ``test_data`` rows ([user, pos...] lists) in device CSR form."""
+    row_user: torch.Tensor      # int64 [n_rows]  (device)
+    rowptr: torch.Tensor        # int64 [n_rows+1] (device)
+    col: torch.Tensor           # int64 [nnz] global ids, sorted inside each row (device)
+    n_pos: np.ndarray           # int32 [n_rows] len(data[1:]) incl. duplicates (host)
+
+
+_pos_cache: Dict[int, Tuple[int, PositivesCSR]] = {}
+
+
+def build_positives_csr(data: Sequence[Sequence[int]], device: torch.device) -> PositivesCSR:
+    key = id(data)
+    hit = _pos_cache.get(key)
+    if hit is not None and hit[0] == len(data) and hit[1].rowptr.device == device:
+        return hit[1]
+    n = len(data)
+    lens = np.fromiter((len(r) - 1 for r in data), dtype=np.int64, count=n)
+    flat = np.fromiter((v for r in data for v in r), dtype=np.int64, count=int(lens.sum()) + n)
+    starts = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens + 1, out=starts[1:])
+    row_user = flat[starts[:-1]]
+    keep = np.ones(flat.shape[0], dtype=bool)
+    keep[starts[:-1]] = False
+    pos = flat[keep]
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=rowptr[1:])
+    row_of = np.repeat(np.arange(n, dtype=np.int64), lens)
+    order = np.lexsort((pos, row_of))
+    out = PositivesCSR(torch.from_numpy(row_user).to(device), torch.from_numpy(rowptr).to(device),
+                       torch.from_numpy(pos[order]).to(device), lens.astype(np.int32))
+    _pos_cache[key] = (n, out)
+    return out
+
+
+def hit_masks(ranklist: torch.Tensor, pos: PositivesCSR) -> torch.Tensor:
+    """uint64-as-int64 [n_rows]: bit r <=> ranked item r of the row's user is a positive."""
+    lib = _lib.load()
+    dev = pos.rowptr.device
+    ranklist = ranklist.to(device=dev, dtype=torch.int64).contiguous()
+    n_rows = int(pos.row_user.numel())
+    K = ranklist.shape[1]
+    out = torch.empty(n_rows, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.chaorec_topk_hits(_lib.ptr(ranklist), _lib.ptr(pos.row_user), _lib.ptr(pos.rowptr), _lib.ptr(pos.col),
+                                   n_rows, K, _lib.ptr(out), _lib.stream_ptr(dev))
+    _lib.check(rc, "chaorec_topk_hits")
+    return out
+
+
+def metrics_from_hits(hits_host: np.ndarray, n_pos: np.ndarray, k_list: Sequence[int]) -> Dict[int, Dict[str, float]]:
+    """Host reduction (sequential fp64, utils.py:116-137) of hit masks into the metrics dict."""
+    lib = _lib.load()
+    ks = np.asarray([int(k) for k in k_list], dtype=np.int32)
+    max_k = int(ks.max()) if ks.size else 0
+    inv_log = np.asarray([1.0 / np.log(i + 2) for i in range(max_k)], dtype=np.float64)  # metrics.py:31,34
+    hits_host = np.ascontiguousarray(hits_host).view(np.uint64)
+    n_pos = np.ascontiguousarray(n_pos, dtype=np.int32)
+    out = np.zeros(len(ks) * 5, dtype=np.float64)
+    rc = lib.chaorec_metrics_from_hits(hits_host.ctypes.data_as(C.c_void_p), n_pos.ctypes.data_as(C.c_void_p),
+                                       int(hits_host.shape[0]), ks.ctypes.data_as(C.c_void_p), int(ks.size),
+                                       inv_log.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    _lib.check(rc, "chaorec_metrics_from_hits")
+    return {k: {name: float(out[t * 5 + j]) for j, name in enumerate(METRIC_NAMES)} for t, k in enumerate(k_list)}
+
+
+def evaluate(model, data, ranklist: torch.Tensor, topk: Sequence[int], device: Optional[torch.device] = None):
+    """Drop-in for ``evaluate(model, data, ranklist, topk)`` (train_and_evaluate.py:516-520).
+
+    ``data``: val/test rows ``[user, pos...]``; ``ranklist``: LongTensor [num_user, >=max(topk)] of
+    global ids (CPU or CUDA).  Returns ``{k: {'precision','recall','ndcg','hit_rate','map'}}``.
+    """
+    if model is not None and hasattr(model, 'eval'):
+        model.eval()
+    if device is None:
+        device = ranklist.device if ranklist.is_cuda else torch.device('cuda', torch.cuda.current_device())
+    if ranklist.shape[1] > 64:
+        ranklist = ranklist[:, :64]
+    pos = build_positives_csr(data, device)
+    hits = hit_masks(ranklist, pos)
+    return metrics_from_hits(hits.cpu().numpy(), pos.n_pos, list(topk))
+
+
+def evaluate_full(user_emb: torch.Tensor, item_emb: torch.Tensor, mask: Optional[MaskCSR], splits: Sequence,
+                  k_list: Sequence[int], topk: int = 50, mask_value: float = 1e-6, id_offset: Optional[int] = None):
+    """Fused evaluation: one ranking pass, then metrics for every split (val, test, ...)."""
+    if id_offset is None:
+        id_offset = user_emb.shape[0]
+    ranks = rank_topk(user_emb, item_emb, mask, topk, mask_value, id_offset)
+    return ranks, [evaluate(None, s, ranks, k_list, device=ranks.device) for s in splits]

@@ -1,0 +1,168 @@
+/*
+ * chaorec_b200.h -- C ABI of the B200-native hot path of ChaoRec.
+ *
+ * The reference (Ricardo-Ping/ChaoRec) is pure Python and has no FFI; its "operator API" for
+ * this path is three Python call seams.  Each entry point below names the
+ * reference call it replaces (paths relative to the reference checkout).  The Python shims in
+ * chaorec_b200/ bind these symbols with ctypes (see INTEGRATION.md for the reference-side
+ * stubs a maintainer would add).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes, no torch types; every pointer is a DEVICE pointer on the
+ *     current CUDA device unless the parameter is documented as host memory;
+ *   - the caller owns every buffer (outputs and workspace); the library never allocates;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no internal sync;
+ *   - return 0 on success, a negative CHAOREC_E_* code on bad arguments or launch failure;
+ *   - stateless and re-entrant; there is no CPU fallback of any kind.
+ */
+#ifndef CHAOREC_B200_H_
+#define CHAOREC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHAOREC_ABI_VERSION 1
+
+enum {
+    CHAOREC_OK = 0,
+    CHAOREC_E_BADARG = -1,       /* null pointer / negative size / inconsistent sizes            */
+    CHAOREC_E_UNSUPPORTED = -2,  /* d not a multiple of 4, K out of range, ...                   */
+    CHAOREC_E_WORKSPACE = -3,    /* workspace too small                                          */
+    CHAOREC_E_LAUNCH = -4,       /* a CUDA call failed (the sticky error is cleared)             */
+    CHAOREC_E_ALIGN = -5         /* a pointer that must be 16-byte aligned is not                */
+};
+
+int chaorec_abi_version(void);
+const char *chaorec_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Propagation:  y = diag(row_scale) * A * diag(col_scale) * x   (+ fused layer mean)
+ * ---------------------------------------------------------------------------------------- */
+
+/*
+ * COO -> CSR (stable by row, then column; duplicates are kept and therefore summed by the
+ * SpMM exactly as torch.sparse.mm sums an uncoalesced tensor, Model/FREEDOM.py:83,162,174).
+ * row/col: int64 [nnz] as stored in torch.sparse_coo_tensor.indices(); val nullable (=> ones).
+ * Outputs: rowptr int64 [M+1], out_col int32 [nnz], out_val float [nnz] (ignored if val NULL).
+ */
+size_t chaorec_coo_to_csr_workspace_bytes(int64_t nnz, int64_t M);
+int chaorec_coo_to_csr(const int64_t *row, const int64_t *col, const float *val, int64_t nnz, int64_t M,
+                       int64_t N, int64_t *rowptr, int32_t *out_col, float *out_val, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/*
+ * out[r] = (rowptr[r+1]-rowptr[r] + eps)^-1/2 in fp32 (inf for an empty row when eps == 0):
+ * deg.pow(-0.5) of Model/LightGCN.py:36-37; with eps = 1e-7 the V3 form of
+ * Model/FREEDOM.py:91-96.
+ */
+int chaorec_degree_inv_sqrt(const int64_t *rowptr, int64_t M, float eps, float *out, void *stream);
+
+/* Rows with more than this many non-zeros are "hub rows"; see chaorec_spmm_csr_f32. */
+int32_t chaorec_spmm_hub_threshold(void);
+int32_t chaorec_spmm_hub_chunk(void);
+
+/*
+ * CSR SpMM, fp32.  Replaces torch.sparse.mm(adj, x) (Model/FREEDOM.py:168,174 and the 36
+ * call sites of SURVEY.md App-A) and LightGCNConv.propagate (Model/LightGCN.py:28-46).
+ *
+ *   y[r,:] = row_scale[r] * sum_{e in row r} val[e] * col_scale[col[e]] * x[col[e],:]
+ *
+ * val / row_scale / col_scale are nullable (=> 1).  y is nullable (skip the store when only
+ * the layer mean is wanted).  Layer-mean fusion (Model/LightGCN.py:86-93,
+ * Model/FREEDOM.py:177-178): if acc != NULL
+ *     acc_mode 0:  acc[r,:] += alpha * y[r,:]
+ *     acc_mode 1:  acc[r,:]  = alpha * x[r,:] + alpha * y[r,:]     (first layer; needs M == N)
+ * Hub rows (nnz > chaorec_spmm_hub_threshold()) are split into chunks of
+ * chaorec_spmm_hub_chunk() edges reduced through shared memory by whole CTAs: pass the
+ * sorted list hub_rows[n_hub], hub_chunk_ptr[n_hub+1] (exclusive prefix of per-row chunk
+ * counts) and hub_partials (float [hub_chunk_ptr[n_hub] * d]).  With hub_rows == NULL every
+ * row takes the sub-warp path (correct, slow for very long rows).
+ * d must be a multiple of 4 and <= 512; x, y, acc 16-byte aligned.
+ */
+int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float *val, const float *row_scale,
+                         const float *col_scale, const float *x, float *y, float *acc, float alpha,
+                         int32_t acc_mode, const int32_t *hub_rows, const int64_t *hub_chunk_ptr,
+                         int32_t n_hub, int64_t n_hub_chunks, float *hub_partials, int64_t M, int64_t N,
+                         int32_t d, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) Full-ranking evaluation
+ * ---------------------------------------------------------------------------------------- */
+
+/*
+ * Fused score + train-mask + top-K.  Replaces the body of gene_ranklist
+ * (Model/LightGCN.py:137-162; batched form Model/MMGCN.py:204-244): the U x I score matrix is
+ * never written to memory.
+ *   score(u,i) = fp32 fmaf chain over k = 0..d-1 of user_emb[u][k]*item_emb[i][k] (from +0)
+ *   masked (u,i) pairs (CSR mask_rowptr int64 [U+1] / mask_col int32, LOCAL item ids, sorted
+ *   ascending and unique inside each row) score exactly mask_value (1e-6f; 1e-5f in
+ *   Model/GRCN.py:294, Model/MMGCN.py:227, Model/LightGT.py:394)
+ *   order: descending score, ties -> ascending item index.
+ * out_idx int64 [U*K] = local item id + id_offset (num_user: Model/LightGCN.py:157-159);
+ * out_score float [U*K] nullable.  1 <= K <= 64, K <= I, d % 4 == 0.
+ * mask_rowptr == NULL => nothing masked.
+ */
+size_t chaorec_score_mask_topk_workspace_bytes(int64_t U, int64_t I, int32_t d, int32_t K);
+int chaorec_score_mask_topk_f32(const float *user_emb, const float *item_emb, const int64_t *mask_rowptr,
+                                const int32_t *mask_col, float mask_value, int64_t U, int64_t I, int32_t d,
+                                int32_t K, int64_t id_offset, int64_t *out_idx, float *out_score,
+                                void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Hit masks for utils.gene_metrics (utils.py:112-139), one per val_data row: bit r of
+ * hit_mask[row] is set iff topk_idx[user*K + r] (user = row_user[row], or row itself when
+ * row_user == NULL: utils.py:117-119) occurs in the row's positives
+ * pos_col[pos_rowptr[row] .. pos_rowptr[row+1]) (global ids, sorted ascending).  K <= 64.
+ */
+int chaorec_topk_hits(const int64_t *topk_idx, const int64_t *row_user, const int64_t *pos_rowptr,
+                      const int64_t *pos_col, int64_t n_rows, int32_t K, uint64_t *hit_mask, void *stream);
+
+/*
+ * HOST function (all pointers are host memory).  The five metrics of metrics.py:13-57 summed
+ * sequentially in fp64 over the rows in order and divided by n_rows, exactly as
+ * utils.py:116-137 does with python floats.
+ *   hit_mask[n_rows]      output of chaorec_topk_hits copied to the host
+ *   n_pos_of_row[n_rows]  len(data[1:]) including duplicates (metrics.py:23,31,57)
+ *   inv_log[max_k]        1.0/np.log(i+2) computed by numpy on the host (metrics.py:31,34)
+ *   out[n_k*5]            precision, recall, ndcg, hit_rate, map for each k
+ */
+int chaorec_metrics_from_hits(const uint64_t *hit_mask, const int32_t *n_pos_of_row, int64_t n_rows,
+                              const int32_t *ks, int32_t n_k, const double *inv_log, double *out);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) Modality item-item cosine kNN graph
+ * ---------------------------------------------------------------------------------------- */
+
+/* norms[i] = (float)sqrt(sum_k (double)x[i][k]^2) (k ascending, fp64); out[i][:] = x[i][:] / norms[i]
+ * (Model/FREEDOM.py:114).  out float [N*D], norms float [N]; both are outputs. */
+int chaorec_l2_normalize_f32(const float *x, int64_t N, int32_t D, float *out, float *norms, void *stream);
+
+/*
+ * Cosine top-k.  Replaces `torch.topk(build_sim(x), k)` (Model/FREEDOM.py:114-118,
+ * Model/LATTICE.py:46-48,68-75, Model/MGCN.py:16-19,58; self excluded:
+ * gen_hypergraph_u_i.py:41-46).  Rows [row_lo,row_hi) of the N x N similarity only (item-row
+ * sharding across GPUs); out_val float / out_idx int64 are [(row_hi-row_lo)*k], values
+ * descending, ties -> ascending column.  The N x N matrix is never materialised.
+ * feats: float [N*D] row-major, D % 4 == 0.  1 <= k <= 64.
+ */
+size_t chaorec_knn_workspace_bytes(int64_t N, int32_t D, int32_t k);
+int chaorec_knn_cosine_topk(const float *feats, int64_t N, int32_t D, int32_t k, int exclude_self,
+                            int64_t row_lo, int64_t row_hi, float *out_val, int64_t *out_idx, void *workspace,
+                            size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Roofline probes (used by bench.py to measure the denominators it reports against)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Runs `iters` dependent-free FFMA per thread on every SM; returns 0 and writes the number of
+ * floating-point operations issued to *flops_out (host pointer).  Time it with CUDA events. */
+int chaorec_probe_fp32_fma(int64_t iters, float *sink, double *flops_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHAOREC_B200_H_ */

@@ -1,0 +1,350 @@
+"""CPU restatement of ChaoRec's hot path (propagation, full-rank evaluation, kNN graph).
+
+TEST INFRASTRUCTURE.  Only ``tests/``, ``__graft_entry__.smoke()`` and the CPU legs of
+``bench.py`` may import this module.  Nothing under ``chaorec_b200/`` imports it; the
+product path fails loudly when its CUDA library is missing.
+
+Parity status: the reference ships no tests or golden vectors for this path,
+so the oracle is pinned against the *reference itself*: ``tests/golden/make_golden.py``
+imports the unmodified ``Model/FREEDOM.py``, ``Model/LightGCN.py`` (through
+``oracle/pyg_stub``), ``utils.gene_metrics`` and ``gen_hypergraph_u_i.get_knn_adj_mat`` from
+``/root/reference`` in the authoring container, runs them on seeded inputs and stores the
+outputs under ``tests/golden``; ``tests/test_oracle_golden.py`` checks every function below
+against those files.
+
+Every function cites the reference lines it follows (paths relative to /root/reference).
+The arithmetic is kept in the same torch CPU operators the reference calls, so the
+restatement is the reference's CPU path minus the nn.Module plumbing.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+# ----------------------------------------------------------------------------------------
+# (1) propagation
+# ----------------------------------------------------------------------------------------
+
+
+def symmetrise_edges(train_edges: np.ndarray | torch.Tensor) -> torch.Tensor:
+    """[E,2] (user, global item id) -> [2,2E]: first E columns u->i, last E columns i->u.
+
+    Model/LightGCN.py:63-64 and Model/FREEDOM.py:38-39.
+    """
+    e = torch.as_tensor(np.asarray(train_edges)).t().contiguous()
+    return torch.cat((e, e[[1, 0]]), dim=1)
+
+
+def pyg_lightgcn_conv(x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+    """One LightGCNConv layer, Model/LightGCN.py:28-46 (same as Model/LATTICE.py:23-42).
+
+    deg = degree(row); norm = deg^-1/2[row] * deg^-1/2[col]; out[col] += norm * x[row].
+    """
+    ei = edge_index.long()
+    src, dst = ei[0], ei[1]
+    deg = torch.zeros(x.size(0), dtype=x.dtype).scatter_add_(0, src, torch.ones(src.numel(), dtype=x.dtype))
+    dis = deg.pow(-0.5)
+    norm = dis[src] * dis[dst]
+    msg = norm.view(-1, 1) * x[src]
+    return torch.zeros_like(x).index_add_(0, dst, msg)
+
+
+def lightgcn_forward(user_w: torch.Tensor, item_w: torch.Tensor, edge_index: torch.Tensor,
+                     n_layers: int) -> torch.Tensor:
+    """Model/LightGCN.py:76-95: L convs, then sum_l (1/(L+1)) * e_l accumulated from zeros."""
+    x = torch.cat((user_w, item_w), dim=0)
+    layers = [x]
+    for _ in range(n_layers):
+        x = pyg_lightgcn_conv(x, edge_index)
+        layers.append(x)
+    w = 1.0 / len(layers)
+    out = torch.zeros_like(layers[0])
+    for e in layers:
+        out += w * e
+    return out
+
+
+def freedom_norm_adj(edge_index: torch.Tensor, n_nodes: int) -> torch.Tensor:
+    """V2 values, Model/FREEDOM.py:73-83: degree = bincount(cat(row, col)) (twice the true
+    degree on the symmetrised list) -> values are half the textbook D^-1/2 A D^-1/2."""
+    ei = edge_index.long()
+    r, c = ei[0], ei[1]
+    deg = torch.bincount(torch.cat([r, c]))
+    dis = deg.pow(-0.5)
+    return torch.sparse_coo_tensor(ei, dis[r] * dis[c], torch.Size([n_nodes, n_nodes]))
+
+
+def normalize_adj_m(indices: torch.Tensor, adj_size: Sequence[int]) -> torch.Tensor:
+    """V3 values, Model/FREEDOM.py:85-100: (1e-7+rowsum)^-1/2[r] * (1e-7+colsum)^-1/2[c]
+    over the bipartite R block (int64 ones)."""
+    adj = torch.sparse_coo_tensor(indices, torch.ones_like(indices[0]), torch.Size(adj_size))
+    rs = 1e-7 + torch.sparse.sum(adj, -1).to_dense()
+    cs = 1e-7 + torch.sparse.sum(adj.t(), -1).to_dense()
+    return torch.pow(rs, -0.5)[indices[0]] * torch.pow(cs, -0.5)[indices[1]]
+
+
+def freedom_masked_adj(keep_indices: torch.Tensor, num_user: int, num_item: int) -> torch.Tensor:
+    """Model/FREEDOM.py:153-162 for an already-sampled set of kept (user, local item) edges."""
+    ki = keep_indices.clone()
+    vals = normalize_adj_m(ki, (num_user, num_item))
+    ki[1] += num_user
+    n = num_user + num_item
+    return torch.sparse_coo_tensor(torch.cat((ki, torch.flip(ki, [0])), 1), torch.cat((vals, vals)),
+                                   torch.Size([n, n]))
+
+
+def sparse_mm_chain_mean(adj: torch.Tensor, x0: torch.Tensor, n_layers: int) -> torch.Tensor:
+    """Model/FREEDOM.py:171-178: ego chain through torch.sparse.mm, stack -> mean(dim=1)."""
+    ego = x0
+    stack = [ego]
+    for _ in range(n_layers):
+        ego = torch.sparse.mm(adj, ego)
+        stack.append(ego)
+    return torch.stack(stack, dim=1).mean(dim=1, keepdim=False)
+
+
+def freedom_forward(user_w, item_w, adj, mm_adj, n_layers: int, mm_layers: int) -> torch.Tensor:
+    """Model/FREEDOM.py:164-183 -> the cached ``self.result`` [U+I, d]."""
+    h = item_w
+    for _ in range(mm_layers):
+        h = torch.sparse.mm(mm_adj, h)
+    allm = sparse_mm_chain_mean(adj, torch.cat((user_w, item_w), dim=0), n_layers)
+    u_g, i_g = torch.split(allm, [user_w.size(0), item_w.size(0)], dim=0)
+    return torch.cat((u_g, i_g + h), dim=0)
+
+
+# ----------------------------------------------------------------------------------------
+# (2) full-ranking evaluation
+# ----------------------------------------------------------------------------------------
+
+
+def masked_score_matrix(user_t: torch.Tensor, item_t: torch.Tensor, user_item_dict: Dict[int, Iterable[int]],
+                        num_user: int, mask_value: float = 1e-6, row_lo: int = 0) -> torch.Tensor:
+    """Model/LightGCN.py:147-152: S = U I^T (CPU fp32), then S[u][train items - U] = 1e-6."""
+    s = torch.matmul(user_t, item_t.t())
+    hi = row_lo + s.size(0)
+    for u, items in user_item_dict.items():
+        if row_lo <= u < hi:
+            cols = torch.LongTensor(list(items)) - num_user
+            s[u - row_lo][cols] = mask_value
+    return s
+
+
+def gene_ranklist(result: torch.Tensor, num_user: int, num_item: int, user_item_dict, topk: int = 50,
+                  mask_value: float = 1e-6, stable: bool = False) -> torch.Tensor:
+    """Model/LightGCN.py:137-162.  ``stable=False`` is the reference verbatim (torch.topk,
+    tie order unspecified); ``stable=True`` applies the stated tie-break (descending score,
+    ties -> ascending item index) through a stable descending sort."""
+    u = result[:num_user].cpu()
+    i = result[num_user:num_user + num_item].cpu()
+    s = masked_score_matrix(u, i, user_item_dict, num_user, mask_value)
+    if stable:
+        idx = torch.sort(s, dim=1, descending=True, stable=True)[1][:, :topk]
+    else:
+        idx = torch.topk(s, topk)[1]
+    return idx + num_user
+
+
+def gene_ranklist_batched(result, num_user, num_item, user_item_dict, step: int = 200, topk: int = 50,
+                          mask_value: float = 1e-5, stable: bool = False) -> torch.Tensor:
+    """Model/MMGCN.py:204-244 user-batched form (the only form that can run at 1M users)."""
+    u = result[:num_user].cpu()
+    i = result[num_user:num_user + num_item].cpu()
+    by_user = user_item_dict
+    out = []
+    lo = 0
+    while lo < num_user:
+        hi = min(lo + step, num_user)
+        s = torch.matmul(u[lo:hi], i.t())
+        for r in range(lo, hi):
+            items = by_user.get(r)
+            if items is not None:
+                s[r - lo][torch.LongTensor(list(items)) - num_user] = mask_value
+        if stable:
+            out.append(torch.sort(s, dim=1, descending=True, stable=True)[1][:, :topk] + num_user)
+        else:
+            out.append(torch.topk(s, topk)[1] + num_user)
+        lo = hi
+    return torch.cat(out, dim=0)
+
+
+def user_metrics_at_k(ranked: List[int], positives: List[int], k: int, inv_log) -> Tuple[float, float, float, int, float]:
+    """(precision, recall, ndcg, hit_rate, map)@k for one user, metrics.py:13-57.
+
+    ``inv_log[i] = 1.0 / np.log(i + 2)`` (natural log, metrics.py:31,34).
+    """
+    top = ranked[:k]
+    pos_set = set(positives)
+    inter = len(set(top) & pos_set)
+    precision = inter / k                                            # metrics.py:16
+    recall = 0 if len(positives) == 0 else inter / len(positives)    # metrics.py:20-23
+    hit = int(bool(inter))                                           # metrics.py:44
+    if not positives:                                                # metrics.py:28, :49
+        return precision, recall, 0, hit, 0
+    idcg = sum([inv_log[i] for i in range(min(len(positives), k))])  # metrics.py:31
+    dcg = 0
+    ap = 0
+    n_hit = 0
+    for pos, item in enumerate(top):
+        if item in positives:
+            dcg += inv_log[pos]                                      # metrics.py:32-34
+            n_hit += 1
+            ap += n_hit / (pos + 1)                                  # metrics.py:53-56
+    return precision, recall, dcg / idcg, hit, ap / len(positives)
+
+
+def gene_metrics(val_data, rank_list, k_list) -> Dict[int, Dict[str, float]]:
+    """utils.py:112-139: sequential python-float sums in ``val_data`` order, / len(val_data)."""
+    inv_log = [1.0 / np.log(i + 2) for i in range(max(k_list) if len(k_list) else 0)]
+    names = ('precision', 'recall', 'ndcg', 'hit_rate', 'map')
+    acc = {k: {n: 0 for n in names} for k in k_list}
+    for row in val_data:
+        user, positives = row[0], row[1:]
+        ranked = rank_list[user].tolist()
+        for k in k_list:
+            vals = user_metrics_at_k(ranked, positives, int(k), inv_log)
+            for n, v in zip(names, vals):
+                acc[k][n] += v
+    n_users = len(val_data)
+    for k in k_list:
+        for n in names:
+            acc[k][n] /= n_users
+    return acc
+
+
+# ----------------------------------------------------------------------------------------
+# (3) modality item-item kNN graph
+# ----------------------------------------------------------------------------------------
+
+
+def build_sim(context: torch.Tensor) -> torch.Tensor:
+    """Model/LATTICE.py:68-75 / Model/FREEDOM.py:114-116: rows / ||row||_2, then X X^T."""
+    cn = context.div(torch.norm(context, p=2, dim=-1, keepdim=True))
+    return torch.mm(cn, cn.transpose(1, 0))
+
+
+def knn_laplacian_ones(indices: torch.Tensor, adj_size) -> torch.Tensor:
+    """Model/FREEDOM.py:130-140: ones -> (1e-7+rowsum)^-1/2[r] * (1e-7+rowsum)^-1/2[c]."""
+    adj = torch.sparse_coo_tensor(indices, torch.ones_like(indices[0]), adj_size)
+    rs = 1e-7 + torch.sparse.sum(adj, -1).to_dense()
+    ris = torch.pow(rs, -0.5)
+    return torch.sparse_coo_tensor(indices, ris[indices[0]] * ris[indices[1]], adj_size)
+
+
+def knn_conv_a(feats: torch.Tensor, k: int, stable: bool = False):
+    """Model/FREEDOM.py:111-128 (self included): -> (indices [2,N*k], sparse adj)."""
+    sim = build_sim(feats)
+    if stable:
+        ind = torch.sort(sim, dim=-1, descending=True, stable=True)[1][:, :k]
+    else:
+        ind = torch.topk(sim, k, dim=-1)[1]
+    rows = torch.arange(ind.shape[0]).unsqueeze(1).expand(-1, k)
+    indices = torch.stack((rows.flatten(), ind.flatten()), 0)
+    return indices, knn_laplacian_ones(indices, sim.size())
+
+
+def knn_conv_b(feats: torch.Tensor, k: int):
+    """Model/LATTICE.py:46-52: top-k values kept -> (knn_val, knn_ind, dense scatter)."""
+    sim = build_sim(feats)
+    val, ind = torch.topk(sim, k, dim=-1)
+    return val, ind, torch.zeros_like(sim).scatter_(-1, ind, val)
+
+
+def dense_sym_laplacian(adj: torch.Tensor) -> torch.Tensor:
+    """Model/LATTICE.py:56-64 as written (diagflat + two dense GEMMs)."""
+    rs = torch.sum(adj, -1)
+    dis = torch.pow(rs, -0.5)
+    dis[torch.isinf(dis)] = 0.
+    dm = torch.diagflat(dis)
+    return torch.mm(torch.mm(dm, adj), dm)
+
+
+def knn_conv_c(feats: torch.Tensor, k: int) -> torch.Tensor:
+    """gen_hypergraph_u_i.py:41-48 (self excluded by -inf on the diagonal) -> knn_ind."""
+    sim = build_sim(feats)
+    sim.fill_diagonal_(-float('inf'))
+    return torch.topk(sim, k, dim=-1)[1]
+
+
+# ----------------------------------------------------------------------------------------
+# Seeded synthetic inputs.  Shared by tests and bench so that the CUDA path
+# and the oracle see identical bytes.
+# ----------------------------------------------------------------------------------------
+
+
+def zipf_item_sampler(num_item: int, gen: torch.Generator):
+    """Zipf(alpha=1) over a random permutation of the items -> (cdf, perm)."""
+    w = 1.0 / torch.arange(1, num_item + 1, dtype=torch.float64)
+    cdf = torch.cumsum(w / w.sum(), 0)
+    perm = torch.randperm(num_item, generator=gen)
+    return cdf, perm
+
+
+def synth_interactions(num_user: int, num_item: int, n_edges: int, seed: int, min_deg: int = 3):
+    """Unique (user, local item) pairs: users uniform with >= min_deg each, items Zipf.
+
+    Returns int64 tensors (user, item) sorted by (user, item), deduplicated.  The edge count
+    after dedup is a little below ``n_edges``.
+    """
+    g = torch.Generator().manual_seed(seed)
+    cdf, perm = zipf_item_sampler(num_item, g)
+    base = torch.arange(num_user, dtype=torch.int64).repeat_interleave(min_deg)
+    extra_n = max(n_edges - base.numel(), 0)
+    extra = torch.randint(0, num_user, (extra_n,), generator=g, dtype=torch.int64)
+    users = torch.cat((base, extra))
+    r = torch.rand(users.numel(), generator=g, dtype=torch.float64)
+    items = perm[torch.searchsorted(cdf, r).clamp_(max=num_item - 1)]
+    key = torch.unique(users * num_item + items)
+    return key // num_item, key % num_item
+
+
+def synth_holdout(num_user: int, num_item: int, train_u: torch.Tensor, train_i: torch.Tensor, n_pos: int,
+                  seed: int):
+    """Per user ``n_pos`` held-out items not in train (val/test positives) -> [U, n_pos] local ids
+    (a clash with a train item is re-drawn a few times, then moved to the next free id)."""
+    g = torch.Generator().manual_seed(seed)
+    train_keys = (train_u * num_item + train_i).numpy()
+    train_set = np.sort(train_keys)
+    out = torch.randint(0, num_item, (num_user, n_pos), generator=g, dtype=torch.int64).numpy()
+    uu = np.arange(num_user, dtype=np.int64)[:, None]
+    for _ in range(64):
+        keys = uu * num_item + out
+        pos = np.searchsorted(train_set, keys)
+        pos[pos == train_set.size] = 0
+        clash = train_set[pos] == keys
+        for j in range(1, n_pos):  # no duplicate positives inside a row
+            for jj in range(j):
+                clash[:, j] |= out[:, j] == out[:, jj]
+        if not clash.any():
+            break
+        out[clash] = (out[clash] + 1) % num_item
+    return torch.from_numpy(out)
+
+
+def to_reference_formats(num_user, train_u, train_i, heldout):
+    """-> (train [E,2] int32 global ids, user_item_dict {u: [global ids]}, val_data object array of
+    [user, pos...] lists) in the layouts dataload.data_load returns (dataload.py:21-58)."""
+    train = torch.stack((train_u, train_i + num_user), 1).to(torch.int32).numpy()
+    d: Dict[int, List[int]] = {}
+    for u, i in train.tolist():
+        d.setdefault(u, []).append(i)
+    rows = np.empty(heldout.shape[0], dtype=object)
+    held = (heldout + num_user).tolist()
+    for u in range(heldout.shape[0]):
+        rows[u] = [u] + held[u]
+    return train, d, rows
+
+
+def xavier_embeddings(n: int, d: int, seed: int) -> torch.Tensor:
+    """nn.init.xavier_uniform_ on an [n,d] table (Model/LightGCN.py:69-70)."""
+    g = torch.Generator().manual_seed(seed)
+    bound = math.sqrt(6.0 / (n + d))
+    return (torch.rand(n, d, generator=g) * 2 - 1) * bound
+
+
+def normal_embeddings(n: int, d: int, seed: int, std: float = 0.1) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, d, generator=g) * std

@@ -1,0 +1,68 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=True)
+
+
+def rows_to_object_array(rows):
+    out = np.empty(len(rows), dtype=object)
+    for i, r in enumerate(rows):
+        out[i] = [int(v) for v in r]
+    return out
+
+
+def unflatten_rows(flat):
+    rows, p = [], 0
+    flat = [int(v) for v in flat]
+    while p < len(flat):
+        n = flat[p]
+        rows.append(flat[p + 1:p + 1 + n])
+        p += 1 + n
+    return rows_to_object_array(rows)
+
+
+def dict_from_train(train):
+    d = {}
+    for u, i in np.asarray(train).tolist():
+        d.setdefault(int(u), []).append(int(i))
+    return d
+
+
+def metrics_array(m, ks):
+    return np.array([[m[int(k)][n] for n in ('precision', 'recall', 'ndcg', 'hit_rate', 'map')] for k in ks],
+                    dtype=np.float64)
+
+
+@pytest.fixture(scope="session")
+def canon():
+    from oracle.canon_py import Canon
+    return Canon()
