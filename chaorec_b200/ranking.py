@@ -213,3 +213,44 @@ def evaluate_full(user_emb: torch.Tensor, item_emb: torch.Tensor, mask: Optional
         id_offset = user_emb.shape[0]
     ranks = rank_topk(user_emb, item_emb, mask, topk, mask_value, id_offset)
     return ranks, [evaluate(None, s, ranks, k_list, device=ranks.device) for s in splits]
+
+
+@dataclass
+class HostEvalBatch:
+    """One evaluation job in HOST (pinned) memory: what a reference-side caller holds after
+    ``model.result.cpu()`` (Model/LightGCN.py:140-141) plus the CSR forms of its python inputs."""
+    user_emb: torch.Tensor      # float32 [U_local, d]
+    item_emb: torch.Tensor      # float32 [I, d]
+    mask_rowptr: torch.Tensor   # int64 [U_local+1]
+    mask_col: torch.Tensor      # int32 [nnz]
+    pos_rowptr: torch.Tensor    # int64 [U_local+1]  (row r <-> local user r)
+    pos_col: torch.Tensor       # int64 [nnz] global ids, sorted inside rows
+    n_pos: np.ndarray           # int32 [U_local]
+    id_offset: int              # num_user
+
+    def pin(self) -> "HostEvalBatch":
+        for name in ("user_emb", "item_emb", "mask_rowptr", "mask_col", "pos_rowptr", "pos_col"):
+            setattr(self, name, getattr(self, name).contiguous().pin_memory())
+        return self
+
+    def h2d_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.user_emb, self.item_emb, self.mask_rowptr,
+                                                          self.mask_col, self.pos_rowptr, self.pos_col))
+
+
+def evaluate_host_batch(batch: HostEvalBatch, topk: int, device: torch.device, mask_value: float = 1e-6):
+    """Host buffers in, hit masks out: H2D copies, fused ranking, hit masks, D2H -- the part of an
+    end-to-end evaluation that runs per rank.  Returns (hits int64 numpy [U_local], d2h bytes)."""
+    ue = batch.user_emb.to(device, non_blocking=True)
+    ie = batch.item_emb.to(device, non_blocking=True)
+    mask = MaskCSR(batch.mask_rowptr.to(device, non_blocking=True), batch.mask_col.to(device, non_blocking=True))
+    pos = PositivesCSR(None, batch.pos_rowptr.to(device, non_blocking=True), batch.pos_col.to(device, non_blocking=True),
+                       batch.n_pos)
+    ranks = rank_topk(ue, ie, mask, topk, mask_value, batch.id_offset)
+    lib = _lib.load()
+    hits = torch.empty(ue.shape[0], dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        rc = lib.chaorec_topk_hits(_lib.ptr(ranks), None, _lib.ptr(pos.rowptr), _lib.ptr(pos.col), ue.shape[0], int(topk),
+                                   _lib.ptr(hits), _lib.stream_ptr(device))
+    _lib.check(rc, "chaorec_topk_hits")
+    return hits

@@ -1,0 +1,120 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, the
+host metric reduction reproduces the reference's numbers, and the host-side data-format logic
+(dict / object arrays -> CSR) is right.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import chaorec_b200 as cb
+from chaorec_b200 import _lib
+from conftest import ROOT, dict_from_train, load_golden, metrics_array, rows_to_object_array, unflatten_rows
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "chaorec_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(chaorec_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_abi_version_and_error_strings():
+    lib = _lib.load()
+    assert lib.chaorec_abi_version() == 1
+    assert lib.chaorec_error_string(0) == b"ok"
+    for code in (-1, -2, -3, -4, -5):
+        assert len(lib.chaorec_error_string(code)) > 4
+    assert lib.chaorec_spmm_hub_chunk() >= lib.chaorec_spmm_hub_threshold() > 0
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cb.rank_topk(torch.zeros(4, 64), torch.zeros(8, 64), None, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cb.knn_topk(torch.zeros(8, 64), 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cb.csr_from_coo(torch.zeros(3, dtype=torch.int64), torch.zeros(3, dtype=torch.int64), None, 4, 4)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "chaorec_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), fn
+
+
+def _hits_numpy(ranklist, rows, K):
+    out = np.zeros(len(rows), dtype=np.uint64)
+    for r, row in enumerate(rows):
+        pos = set(row[1:])
+        bits = 0
+        for j, item in enumerate(ranklist[row[0]][:K].tolist()):
+            if item in pos:
+                bits |= 1 << j
+        out[r] = bits
+    return out
+
+
+def test_host_metrics_reproduce_reference_exactly():
+    g = load_golden("lightgcn_small.npz")
+    ks = [int(k) for k in g["ks"]]
+    for rows_key, m_key in (("val_rows", "metrics_val"), ("test_rows", "metrics_test")):
+        rows = rows_to_object_array(g[rows_key])
+        hits = _hits_numpy(g["ranklist"], rows, 50)
+        n_pos = np.array([len(r) - 1 for r in rows], dtype=np.int32)
+        m = cb.metrics_from_hits(hits, n_pos, ks)
+        assert metrics_array(m, ks).tolist() == g[m_key].tolist()
+    a = load_golden("metrics_adversarial.npz")
+    ks = [int(k) for k in a["ks"]]
+    rows = unflatten_rows(a["rows_flat"])
+    hits = _hits_numpy(a["ranklist"], rows, 50)
+    m = cb.metrics_from_hits(hits, np.array([len(r) - 1 for r in rows], dtype=np.int32), ks)
+    assert metrics_array(m, ks).tolist() == a["metrics"].tolist()
+    assert isinstance(m[ks[0]]["ndcg"], float)
+
+
+def test_host_metrics_empty_positive_rows():
+    hits = np.zeros(3, dtype=np.uint64)
+    m = cb.metrics_from_hits(hits, np.array([0, 2, 0], dtype=np.int32), [5])
+    assert m[5] == {'precision': 0.0, 'recall': 0.0, 'ndcg': 0.0, 'hit_rate': 0.0, 'map': 0.0}
+
+
+def test_mask_csr_from_user_item_dict():
+    g = load_golden("lightgcn_small.npz")
+    U, I = int(g["num_user"]), int(g["num_item"])
+    uid = dict_from_train(g["train"])
+    uid[3] = list(uid[3]) + [uid[3][0]]            # duplicate
+    uid[5] = list(uid[5]) + [U + I + 7, U - 1]     # out of range on both sides
+    m = cb.build_mask_csr(uid, U, I, torch.device("cpu"))
+    rp, col = m.rowptr.numpy(), m.col.numpy()
+    assert rp[0] == 0 and rp[-1] == col.size and col.dtype == np.int32
+    for u in range(U):
+        want = sorted(set(i - U for i in uid.get(u, []) if U <= i < U + I))
+        assert col[rp[u]:rp[u + 1]].tolist() == want
+    m2 = cb.mask_csr_from_edges(torch.from_numpy(g["train"][:, 0].astype(np.int64)),
+                                torch.from_numpy(g["train"][:, 1].astype(np.int64) - U), U, I)
+    m0 = cb.build_mask_csr(dict_from_train(g["train"]), U, I, torch.device("cpu"))
+    assert torch.equal(m2.rowptr, m0.rowptr) and torch.equal(m2.col, m0.col)
+
+
+def test_positives_csr_from_val_rows():
+    a = load_golden("metrics_adversarial.npz")
+    rows = unflatten_rows(a["rows_flat"])
+    p = cb.build_positives_csr(rows, torch.device("cpu"))
+    assert p.row_user.tolist() == [r[0] for r in rows]
+    assert p.n_pos.tolist() == [len(r) - 1 for r in rows]
+    rp = p.rowptr.numpy()
+    for i, r in enumerate(rows):
+        assert p.col[rp[i]:rp[i + 1]].tolist() == sorted(r[1:])

@@ -1,0 +1,109 @@
+"""GPU parity of the modality kNN graph (csrc/rank_topk.cu kNN entry) through the C ABI.
+
+Bar: neighbour indices (and their order) bit-exact against the canonical oracle and against the
+reference's own outputs under tests/golden; kept similarities bit-exact against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import chaorec_b200 as cb
+from conftest import load_golden
+from oracle import ref_ops
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def test_reference_fixture_conventions_a_and_c():
+    g = load_golden("freedom_small.npz")
+    for mod in ("v", "t"):
+        feats = torch.from_numpy(g[f"{mod}_feat"]).to(dev())
+        indices, adj = cb.get_knn_adj_mat(feats, 10)                    # Model/FREEDOM.py:63,66
+        assert indices.dtype == torch.int64
+        assert torch.equal(indices.cpu(), torch.from_numpy(g[f"knn_a_{mod}_indices"]))
+        assert adj.layout == torch.sparse_coo and tuple(adj.shape) == (feats.shape[0], feats.shape[0])
+        # O(N*k) torch post-processing on the GPU: pow(-0.5) may differ from the CPU's by an ulp
+        assert torch.allclose(adj._values().cpu(), torch.from_numpy(g[f"knn_a_{mod}_values"]), rtol=1e-6, atol=0)
+    knn_c = cb.knn_self_excluded(torch.from_numpy(g["v_feat"]).to(dev()), 10)   # gen_hypergraph_u_i.py:41
+    assert torch.equal(knn_c.cpu(), torch.from_numpy(g["knn_c_v"]))
+    knn_c5 = cb.knn_self_excluded(torch.from_numpy(g["t_feat"]).to(dev()), 5)
+    assert torch.equal(knn_c5.cpu(), torch.from_numpy(g["knn_c_t"]))
+
+
+def test_l2_normalize_bit_exact(canon):
+    x = torch.relu(torch.randn(777, 384, generator=torch.Generator().manual_seed(1)))
+    x[5] *= 1e-3
+    cn, norms = cb.l2_normalize(x.to(dev()))
+    assert np.array_equal(cn.cpu().numpy().view(np.uint32), canon.l2_normalize(x.numpy()).view(np.uint32))
+    want = np.sqrt((x.double() ** 2).sum(1).numpy()).astype(np.float32)
+    assert np.max(np.abs(norms.cpu().numpy() - want) / want) < 2e-7
+
+
+@pytest.mark.parametrize("N,D,k,excl", [(2500, 384, 10, 0), (1300, 512, 10, 1), (900, 4096, 10, 0), (700, 64, 20, 0),
+                                        (257, 100, 5, 1)])
+def test_seeded_knn_bit_exact_vs_canon(canon, N, D, k, excl):
+    g = torch.Generator().manual_seed(N + D)
+    x = torch.randn(N, D, generator=g)
+    if D >= 512:
+        x = torch.relu(x)                                              # CNN-feature-like, non-negative
+    val, idx = cb.knn_topk(x.to(dev()), k, exclude_self=bool(excl))
+    cval, cidx = canon.knn_cosine_topk(x.numpy(), k, excl)
+    assert np.array_equal(idx.cpu().numpy(), cidx)
+    assert np.array_equal(val.cpu().numpy().view(np.uint32), cval.view(np.uint32))
+    if not excl:
+        assert bool((idx[:, 0].cpu() == torch.arange(N)).all())        # self is rank 0
+
+
+def test_duplicate_rows_tie_break_and_row_sharding(canon):
+    N, D, k = 1200, 384, 10
+    x = torch.randn(N, D, generator=torch.Generator().manual_seed(4))
+    x[300:330] = x[17]                                                 # exact duplicates -> ties at sim == 1
+    val, idx = cb.knn_topk(x.to(dev()), k)
+    cval, cidx = canon.knn_cosine_topk(x.numpy(), k, 0)
+    assert np.array_equal(idx.cpu().numpy(), cidx)
+    assert idx[300].cpu().tolist() == [17] + list(range(300, 309))     # lowest index first among equals
+    # item-row sharding (multi-GPU split): rows [lo, hi) of the same matrix
+    parts = [cb.knn_topk(x.to(dev()), k, row_range=(lo, hi)) for lo, hi in ((0, 400), (400, 401), (401, 1200))]
+    assert torch.equal(torch.cat([p[1] for p in parts]), idx)
+    assert torch.equal(torch.cat([p[0] for p in parts]), val)
+
+
+def test_convention_b_dense_and_sparse_laplacian():
+    feats = torch.randn(300, 64, generator=torch.Generator().manual_seed(6))
+    val_ref, ind_ref, dense_ref = ref_ops.knn_conv_b(feats, 10)
+    dense = cb.build_knn_neighbourhood(feats.to(dev()), 10)            # Model/LATTICE.py:46-52
+    assert torch.equal((dense != 0).cpu(), dense_ref != 0)
+    assert float((dense.cpu() - dense_ref).abs().max()) <= 1e-6
+    val, ind = cb.build_knn_neighbourhood(feats.to(dev()), 10, dense=False)
+    lap = cb.knn_sym_laplacian(val, ind).to_dense().cpu()
+    lap_ref = ref_ops.dense_sym_laplacian(dense_ref)
+    assert float((lap - lap_ref).abs().max()) <= 1e-5 * float(lap_ref.abs().max())
+
+
+def test_clothing_shaped_text_modality_sampled(canon):
+    """BASELINE.json configs[2]: 23,033 items, t_feat 384-d, k=10 -- full build on the GPU, a seeded
+    sample of rows re-derived by the oracle must match bit for bit."""
+    N, D, k = 23033, 384, 10
+    g = torch.Generator().manual_seed(20263)
+    x = torch.randn(N, D, generator=g)
+    x[5000:5230] = x[123]                                              # 1 % exact-duplicate block
+    val, idx = cb.knn_topk(x.to(dev()), k)
+    assert bool((val[:, 1:] <= val[:, :-1]).all())
+    for lo in (0, 5000, 23000):
+        hi = min(lo + 33, N)
+        cval, cidx = canon.knn_cosine_topk(x.numpy(), k, 0, lo, hi)
+        assert np.array_equal(idx[lo:hi].cpu().numpy(), cidx)
+        assert np.array_equal(val[lo:hi].cpu().numpy().view(np.uint32), cval.view(np.uint32))
+
+
+def test_knn_bad_arguments():
+    x = torch.randn(40, 64, device=dev())
+    with pytest.raises(RuntimeError, match="unsupported"):
+        cb.knn_topk(x, 65)
+    with pytest.raises(RuntimeError, match="unsupported"):
+        cb.knn_topk(x[:, :62].contiguous(), 5)
+    with pytest.raises(RuntimeError, match="unsupported"):
+        cb.knn_topk(x, 40, exclude_self=True)

@@ -1,0 +1,204 @@
+"""GPU parity of the propagation path (csrc/spmm.cu, csrc/csr_build.cu) through the C ABI.
+
+Tolerance (north_star): embeddings within 1e-5 relative error in fp32, measured as
+max|delta| / max|reference|.
+"""
+import numpy as np
+import pytest
+import torch
+
+import chaorec_b200 as cb
+from conftest import load_golden
+from oracle import ref_ops
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+def rel_err(got: torch.Tensor, ref: torch.Tensor) -> float:
+    ref = ref.to(torch.float32)
+    return float((got.detach().cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def test_lightgcn_conv_and_forward_match_reference_fixture():
+    g = load_golden("lightgcn_small.npz")
+    x0 = torch.from_numpy(np.concatenate([g["user_w"], g["item_w"]])).to(dev())
+    ei = torch.from_numpy(g["edge_index"]).to(dev())
+    conv = cb.LightGCNConv(64, 64, aggr='add')
+    assert rel_err(conv(x0, ei), torch.from_numpy(g["one_layer"])) <= REL
+    # the reference forward loop with the drop-in conv (Model/LightGCN.py:76-95)
+    embs, x = [x0], x0
+    for _ in range(int(g["n_layers"])):
+        x = conv(x, ei)
+        embs.append(x)
+    final = torch.zeros_like(x0)
+    for e in embs:
+        final += (1.0 / len(embs)) * e
+    assert rel_err(final, torch.from_numpy(g["result"])) <= REL
+    fused = cb.lightgcn_forward(x0[:int(g["num_user"])], x0[int(g["num_user"]):], ei, int(g["n_layers"]))
+    assert rel_err(fused, torch.from_numpy(g["result"])) <= REL
+
+
+def test_freedom_sparse_mm_chain_matches_reference_fixture():
+    g = load_golden("freedom_small.npz")
+    U, I = int(g["num_user"]), int(g["num_item"])
+    n = U + I
+    uw, iw = torch.from_numpy(g["user_w"]).to(dev()), torch.from_numpy(g["item_w"]).to(dev())
+    mm = torch.sparse_coo_tensor(torch.from_numpy(g["mm_adj_idx"]), torch.from_numpy(g["mm_adj_val"]), (I, I)).to(dev())
+    for prefix, key in (("masked_adj", "result_masked"), ("norm_adj", "result_norm")):
+        adj = torch.sparse_coo_tensor(torch.from_numpy(g[prefix + "_idx"]), torch.from_numpy(g[prefix + "_val"]),
+                                      (n, n)).to(dev())      # uncoalesced, like the reference's
+        # Model/FREEDOM.py:164-183 with torch.sparse.mm -> cb.spmm
+        h = iw
+        for _ in range(int(g["mm_layers"])):
+            h = cb.spmm(mm, h)
+        ego = torch.cat((uw, iw), 0)
+        layers = [ego]
+        for _ in range(int(g["n_layers"])):
+            ego = cb.spmm(adj, ego)
+            layers.append(ego)
+        allm = torch.stack(layers, 1).mean(1)
+        res = torch.cat((allm[:U], allm[U:] + h), 0)
+        assert rel_err(res, torch.from_numpy(g[key])) <= REL
+        fused = cb.propagate_mean(adj, torch.cat((uw, iw), 0), int(g["n_layers"]))
+        res2 = torch.cat((fused[:U], fused[U:] + h), 0)
+        assert rel_err(res2, torch.from_numpy(g[key])) <= REL
+
+
+def test_real_graph_slice_matches_reference_fixture():
+    g = load_golden("baby_slice.npz")
+    U, I = int(g["num_user"]), int(g["num_item"])
+    uw = ref_ops.xavier_embeddings(U, 64, int(g["seed_user"])).to(dev())
+    iw = ref_ops.xavier_embeddings(I, 64, int(g["seed_item"])).to(dev())
+    ei = ref_ops.symmetrise_edges(g["train"]).to(dev())
+    out = cb.lightgcn_forward(uw, iw, ei, int(g["n_layers"]))
+    rows = torch.from_numpy(g["check_rows"])
+    err = (out.cpu()[rows] - torch.from_numpy(g["result_rows"])).abs().max() / float(g["result_absmax"])
+    assert float(err) <= REL
+    # isolated nodes: zero rows, no inf/nan leaking out of deg^-1/2
+    assert torch.isfinite(out).all()
+
+
+def _random_coo(M, N, nnz, seed, dup=True):
+    g = torch.Generator().manual_seed(seed)
+    r = torch.randint(0, M, (nnz,), generator=g)
+    c = torch.randint(0, N, (nnz,), generator=g)
+    v = torch.randn(nnz, generator=g)
+    if dup:
+        r = torch.cat((r, r[: nnz // 10]))
+        c = torch.cat((c, c[: nnz // 10]))
+        v = torch.cat((v, torch.randn(nnz // 10, generator=g)))
+    return r, c, v
+
+
+@pytest.mark.parametrize("M,N,d", [(700, 700, 64), (300, 900, 64), (900, 300, 32), (257, 513, 128), (200, 300, 100),
+                                   (150, 150, 384), (64, 64, 512), (1000, 1000, 4)])
+def test_spmm_matches_torch_sparse_mm(M, N, d):
+    r, c, v = _random_coo(M, N, 6000, 100 + d)
+    x = torch.randn(N, d, generator=torch.Generator().manual_seed(7))
+    adj = torch.sparse_coo_tensor(torch.stack((r, c)), v, (M, N))
+    ref = torch.sparse.mm(adj, x)
+    got = cb.spmm(adj.to(dev()), x.to(dev()))
+    assert got.shape == (M, d)
+    assert rel_err(got, ref) <= REL
+
+
+def test_spmm_hub_rows_empty_rows_and_scales():
+    M = N = 3000
+    g = torch.Generator().manual_seed(3)
+    rows = [torch.randint(0, M, (20000,), generator=g), torch.full((30000,), 5), torch.full((1500,), 2999),
+            torch.full((4097,), 17)]
+    r = torch.cat(rows)
+    c = torch.randint(0, N, (r.numel(),), generator=g)
+    r[r == 100] = 101                                   # row 100 is empty
+    v = torch.rand(r.numel(), generator=g)
+    rs, cs = torch.rand(M, generator=g) + 0.5, torch.rand(N, generator=g) + 0.5
+    x = torch.randn(N, 64, generator=g)
+    graph = cb.csr_from_coo(r.to(dev()), c.to(dev()), v.to(dev()), M, N)
+    assert graph.n_hub == 3 and graph.n_hub_chunks == 8 + 1 + 2
+    graph.row_scale, graph.col_scale = rs.to(dev()), cs.to(dev())
+    got = cb.spmm(graph, x.to(dev()))
+    adj = torch.sparse_coo_tensor(torch.stack((r, c)), v.double() * rs.double()[r] * cs.double()[c], (M, N))
+    ref = torch.sparse.mm(adj, x.double())
+    assert rel_err(got, ref) <= REL
+    assert float(got[100].abs().max()) == 0.0
+    # without a hub plan the same rows go through the sub-warp path
+    graph.hub_rows, graph.n_hub, graph.n_hub_chunks = None, 0, 0
+    assert rel_err(cb.spmm(graph, x.to(dev())), ref) <= REL
+
+
+def test_csr_build_is_sorted_and_keeps_duplicates():
+    r, c, v = _random_coo(500, 400, 4000, 11)
+    graph = cb.csr_from_coo(r.to(dev()), c.to(dev()), v.to(dev()), 500, 400)
+    rp, col, val = graph.rowptr.cpu().numpy(), graph.col.cpu().numpy(), graph.val.cpu().numpy()
+    assert rp[0] == 0 and rp[-1] == r.numel() and np.all(np.diff(rp) == np.bincount(r.numpy(), minlength=500))
+    order = np.lexsort((np.arange(r.numel()), c.numpy(), r.numpy()))     # stable by (row, col)
+    assert np.array_equal(col, c.numpy()[order].astype(np.int32))
+    assert np.array_equal(val, v.numpy()[order])
+    empty = cb.csr_from_coo(r[:0].to(dev()), c[:0].to(dev()), None, 7, 7)
+    assert empty.rowptr.tolist() == [0] * 8
+
+
+def test_propagate_mean_variants_and_autograd():
+    U, I, d, L = 400, 300, 64, 3
+    tu, ti = ref_ops.synth_interactions(U, I, 3000, 5)
+    train = torch.stack((tu, ti + U), 1)
+    ei = ref_ops.symmetrise_edges(train.numpy())
+    x0 = ref_ops.xavier_embeddings(U + I, d, 9)
+    # reference-side: autograd through the restated PyG conv on the CPU
+    xr = x0.clone().requires_grad_(True)
+    out_ref = ref_ops.lightgcn_forward(xr[:U], xr[U:], ei, L)
+    w = torch.randn(U + I, d, generator=torch.Generator().manual_seed(1))
+    (out_ref * w).sum().backward()
+    xg = x0.clone().to(dev()).requires_grad_(True)
+    out = cb.lightgcn_forward(xg[:U], xg[U:], ei.to(dev()), L)
+    (out * w.to(dev())).sum().backward()
+    assert rel_err(out, out_ref.detach()) <= REL
+    assert rel_err(xg.grad, xr.grad) <= REL
+    # mean without layer 0 (Model/SimGCL.py:112-120) on an explicit COO adjacency, non-symmetric values
+    n = U + I
+    vals = torch.rand(ei.shape[1], generator=torch.Generator().manual_seed(2))
+    adj = torch.sparse_coo_tensor(ei, vals, (n, n))
+    xr = x0.clone().requires_grad_(True)
+    e, acc = xr, []
+    for _ in range(2):
+        e = torch.sparse.mm(adj, e)
+        acc.append(e)
+    ref = torch.stack(acc, 1).mean(1)
+    (ref * w).sum().backward()
+    xg = x0.clone().to(dev()).requires_grad_(True)
+    got = cb.propagate_mean(adj.to(dev()), xg, 2, include_layer0=False)
+    (got * w.to(dev())).sum().backward()
+    assert rel_err(got, ref.detach()) <= REL
+    assert rel_err(xg.grad, xr.grad) <= REL
+
+
+def test_sports_shaped_propagation_matches_oracle():
+    """BASELINE.json configs[1] shape: 35,598 users x 18,357 items, ~296k interactions, d=64, L=3."""
+    U, I, d, L = 35598, 18357, 64, 3
+    tu, ti = ref_ops.synth_interactions(U, I, 296337, 20262)
+    ei = ref_ops.symmetrise_edges(torch.stack((tu, ti + U), 1).numpy())
+    uw, iw = ref_ops.xavier_embeddings(U, d, 1), ref_ops.xavier_embeddings(I, d, 2)
+    ref = ref_ops.lightgcn_forward(uw, iw, ei, L)
+    got = cb.lightgcn_forward(uw.to(dev()), iw.to(dev()), ei.to(dev()), L)
+    assert rel_err(got, ref) <= REL
+    # FREEDOM's halved V2 matrix through the sparse.mm seam
+    adj = ref_ops.freedom_norm_adj(ei, U + I)
+    ref2 = ref_ops.sparse_mm_chain_mean(adj, torch.cat((uw, iw)), 2)
+    got2 = cb.propagate_mean(adj.to(dev()), torch.cat((uw, iw)).to(dev()), 2)
+    assert rel_err(got2, ref2) <= REL
+
+
+def test_spmm_rejects_bad_shapes():
+    r, c, v = _random_coo(50, 60, 200, 1, dup=False)
+    adj = torch.sparse_coo_tensor(torch.stack((r, c)), v, (50, 60)).to(dev())
+    with pytest.raises(RuntimeError):
+        cb.spmm(adj, torch.zeros(61, 64, device=dev()))
+    with pytest.raises(RuntimeError, match="unsupported"):
+        cb.spmm(adj, torch.zeros(60, 66, device=dev()))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cb.spmm(adj, torch.zeros(60, 64))
