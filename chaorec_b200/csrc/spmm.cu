@@ -247,7 +247,10 @@ __global__ void degree_inv_sqrt_kernel(const int64_t *__restrict__ rowptr, int64
     const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (r >= M) return;
     const float deg = static_cast<float>(rowptr[r + 1] - rowptr[r]) + eps;
-    out[r] = 1.0f / sqrtf(deg);  // IEEE sqrt + division; 0 -> +inf like deg.pow(-0.5)
+    // IEEE sqrt + division.  deg == 0 (isolated node, eps == 0): the reference's deg.pow(-0.5) is
+    // +inf there but no edge ever indexes it; 0 keeps 0 * scale finite in the
+    // kernel epilogue, which does multiply the (all-zero) row sum by its row scale.
+    out[r] = deg > 0.0f ? 1.0f / sqrtf(deg) : 0.0f;
 }
 
 }  // namespace

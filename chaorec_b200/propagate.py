@@ -260,6 +260,7 @@ def graph_from_edge_index(edge_index: torch.Tensor, num_nodes: int) -> CSRGraph:
         g.symmetric = bool(torch.equal(torch.sort(src * num_nodes + dst)[0], torch.sort(dst * num_nodes + src)[0]))
     else:
         dis = src_deg.to(torch.float32).pow(-0.5)
+        dis[torch.isinf(dis)] = 0.0     # isolated nodes: never indexed by an edge, keep 0 * scale finite
     g.row_scale, g.col_scale = dis, dis
     if len(_edge_cache) > 16:
         for k in [k for k, v in _edge_cache.items() if v[0]() is None]:

@@ -55,9 +55,9 @@ int chaorec_coo_to_csr(const int64_t *row, const int64_t *col, const float *val,
                        size_t workspace_bytes, void *stream);
 
 /*
- * out[r] = (rowptr[r+1]-rowptr[r] + eps)^-1/2 in fp32 (inf for an empty row when eps == 0):
- * deg.pow(-0.5) of Model/LightGCN.py:36-37; with eps = 1e-7 the V3 form of
- * Model/FREEDOM.py:91-96.
+ * out[r] = (rowptr[r+1]-rowptr[r] + eps)^-1/2 in fp32: deg.pow(-0.5) of Model/LightGCN.py:36-37;
+ * with eps = 1e-7 the V3 form of Model/FREEDOM.py:91-96.  An empty row with eps == 0 gets 0 (the
+ * reference's +inf is never indexed by an edge; 0 keeps the fused row scaling finite).
  */
 int chaorec_degree_inv_sqrt(const int64_t *rowptr, int64_t M, float eps, float *out, void *stream);
 
