@@ -1,0 +1,35 @@
+// Internal interface between the two top-K engines and the C-ABI entry points.
+#pragma once
+
+#include "common.cuh"
+
+namespace chaorec {
+
+// "For every row of A, the K columns of B with the largest canonical dot product."
+struct EngineArgs {
+    const float *A;   // [Ma, d] fp32
+    const float *B;   // [Nb, d] fp32
+    int64_t Ma, Nb;
+    int d, K;
+    const int64_t *mask_rowptr;   // nullable; indexed by the row of A
+    const int32_t *mask_col;
+    float mask_value;
+    int exclude_self;             // skip column (row + self_off)
+    int64_t self_off;
+    int64_t id_offset;
+    int64_t *out_idx;             // [Ma, K]
+    float *out_score;             // nullable
+    const int32_t *row_list;      // nullable: process only rows row_list[0 .. *row_count_dev)
+    const unsigned int *row_count_dev;
+};
+
+// exact fp32 CUDA-core engine (rank_topk.cu)
+size_t rank_workspace_bytes(int64_t Ma, int d);
+int rank_launch_engine(const EngineArgs &e, void *workspace, size_t workspace_bytes, cudaStream_t stm);
+
+// bf16 tcgen05 pre-filter + exact re-score + certification (tc_candidates.cu)
+bool tc_supported(int64_t Ma, int64_t Nb, int D, int K);
+size_t tc_workspace_bytes(int64_t Ma, int64_t Nb, int D);
+int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes, cudaStream_t stm);
+
+}  // namespace chaorec

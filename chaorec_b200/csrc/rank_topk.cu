@@ -21,7 +21,11 @@
 //     stage) and keeps the best K, raising the row threshold;
 //   * after the last tile the first K masked items (score = mask_value) are merged in, the list
 //     is sorted by (score desc, index asc) and the top K leave as int64 ids (+ id_offset).
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
+#include "engine.cuh"
 
 namespace chaorec {
 namespace {
@@ -56,6 +60,8 @@ struct RankArgs {
     uint64_t *cand;  // [gridDim.x][TU][CAP]
     unsigned int *tile_counter;
     int n_row_tiles;
+    const int32_t *row_list;            // nullable: tile rows are row_list[u0 + r] instead of u0 + r
+    const unsigned int *row_count_dev;  // number of listed rows (device memory)
 };
 
 struct RowState {
@@ -170,23 +176,37 @@ __device__ __forceinline__ void finish_row(const RankArgs &a, RowState *st, uint
     __syncwarp();
 }
 
-// Producer (warp 0): one ring stage = KC-wide slice c of B tile `it` (+ of the A tile when A is
-// not resident).  Rows are copied one by one so that they land on the padded stride.
+// One ring stage = KC-wide slice c of B tile `it` (+ of the A tile when A is not resident).  Rows
+// are copied one by one so that they land on the padded stride.  The copies are spread over the
+// whole CTA (thread r copies B row r, thread 128+r copies A row r): a single producer warp issuing
+// all 128-256 descriptor-less bulk copies lagged its seven sibling warps by the issue time and the
+// CTA barrier then stalled on it (35 % of warp time in the first ncu capture, profiles/r01_*).
+template <bool A_RESIDENT>
+__device__ __forceinline__ uint32_t stage_tx_bytes(const RankArgs &a, int nu, int64_t q, int nch) {
+    const int it = static_cast<int>(q / nch), c = static_cast<int>(q % nch);
+    const int kc = (a.d - c * KC < KC) ? (a.d - c * KC) : KC;
+    const int64_t i0 = static_cast<int64_t>(it) * TI;
+    const int nb = (a.Nb - i0 < TI) ? static_cast<int>(a.Nb - i0) : TI;
+    return static_cast<uint32_t>(nb + (A_RESIDENT ? 0 : nu)) * static_cast<uint32_t>(kc) * 4u;
+}
+
 template <bool A_RESIDENT>
 __device__ __forceinline__ void issue_stage(const RankArgs &a, float *stage, uint64_t *bar, int64_t u0, int nu,
-                                            int it, int c, int lane) {
+                                            int64_t q, int nch, int tid) {
+    const int it = static_cast<int>(q / nch), c = static_cast<int>(q % nch);
     const int kc = (a.d - c * KC < KC) ? (a.d - c * KC) : KC;
     const uint32_t row_bytes = static_cast<uint32_t>(kc) * 4u;
     const int64_t i0 = static_cast<int64_t>(it) * TI;
     const int nb = (a.Nb - i0 < TI) ? static_cast<int>(a.Nb - i0) : TI;
-    if (lane == 0) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(nb + (A_RESIDENT ? 0 : nu)) * row_bytes);
-    __syncwarp();
     float *sB = A_RESIDENT ? stage : stage + kTileFloats;
-    for (int r = lane; r < nb; r += 32)
-        bulk_g2s(sB + r * LDSF, a.B + (i0 + r) * a.d + c * KC, row_bytes, bar);
-    if (!A_RESIDENT) {
-        for (int r = lane; r < nu; r += 32)
-            bulk_g2s(stage + r * LDSF, a.A + (u0 + r) * a.d + c * KC, row_bytes, bar);
+    if (tid < TI) {
+        if (tid < nb) bulk_g2s(sB + tid * LDSF, a.B + (i0 + tid) * a.d + c * KC, row_bytes, bar);
+    } else if (!A_RESIDENT) {
+        const int r = tid - TI;
+        if (r < nu) {
+            const int64_t ar = a.row_list ? static_cast<int64_t>(a.row_list[u0 + r]) : u0 + r;
+            bulk_g2s(stage + r * LDSF, a.A + ar * a.d + c * KC, row_bytes, bar);
+        }
     }
 }
 
@@ -234,6 +254,8 @@ __global__ void __launch_bounds__(kThreads, A_RESIDENT ? 2 : 1) rank_topk_kernel
     const int nch = (a.d + KC - 1) / KC;
     const int n_it = static_cast<int>((a.Nb + TI - 1) / TI);
     const int64_t Q = static_cast<int64_t>(n_it) * nch;
+    const int64_t Ma_eff = a.row_list ? static_cast<int64_t>(*a.row_count_dev) : a.Ma;
+    const int n_row_tiles = a.row_list ? static_cast<int>((Ma_eff + TU - 1) / TU) : a.n_row_tiles;
 
     for (;;) {
         if (tid == 0) *s_tile = static_cast<int>(atomicAdd(a.tile_counter, 1u));
@@ -244,20 +266,23 @@ __global__ void __launch_bounds__(kThreads, A_RESIDENT ? 2 : 1) rank_topk_kernel
         }
         __syncthreads();
         const int ut = *s_tile;
-        if (ut >= a.n_row_tiles) break;
+        if (ut >= n_row_tiles) break;
         const int64_t u0 = static_cast<int64_t>(ut) * TU;
-        const int nu = (a.Ma - u0 < TU) ? static_cast<int>(a.Ma - u0) : TU;
+        const int nu = (Ma_eff - u0 < TU) ? static_cast<int>(Ma_eff - u0) : TU;
 
-        if (warp == 0) {
-            if (A_RESIDENT) {
-                const uint32_t row_bytes = static_cast<uint32_t>(a.d) * 4u;
-                if (lane == 0) mbar_arrive_expect_tx(&bars[2], static_cast<uint32_t>(nu) * row_bytes);
-                __syncwarp();
-                for (int r = lane; r < nu; r += 32) bulk_g2s(sA_res + r * LDSF, a.A + (u0 + r) * a.d, row_bytes, &bars[2]);
-            }
-            issue_stage<A_RESIDENT>(a, stage0, &bars[0], u0, nu, 0, 0, lane);
-            if (Q > 1) issue_stage<A_RESIDENT>(a, stage1, &bars[1], u0, nu, static_cast<int>(1 / nch), static_cast<int>(1 % nch), lane);
+        // expected byte counts first (one thread), then every thread issues its row copies
+        if (tid == 0) {
+            if (A_RESIDENT) mbar_arrive_expect_tx(&bars[2], static_cast<uint32_t>(nu) * static_cast<uint32_t>(a.d) * 4u);
+            mbar_arrive_expect_tx(&bars[0], stage_tx_bytes<A_RESIDENT>(a, nu, 0, nch));
+            if (Q > 1) mbar_arrive_expect_tx(&bars[1], stage_tx_bytes<A_RESIDENT>(a, nu, 1, nch));
         }
+        __syncthreads();
+        if (A_RESIDENT && tid < nu) {
+            const int64_t ar = a.row_list ? static_cast<int64_t>(a.row_list[u0 + tid]) : u0 + tid;
+            bulk_g2s(sA_res + tid * LDSF, a.A + ar * a.d, static_cast<uint32_t>(a.d) * 4u, &bars[2]);
+        }
+        issue_stage<A_RESIDENT>(a, stage0, &bars[0], u0, nu, 0, nch, tid);
+        if (Q > 1) issue_stage<A_RESIDENT>(a, stage1, &bars[1], u0, nu, 1, nch, tid);
         if (A_RESIDENT) {
             mbar_wait(&bars[2], phA);
             phA ^= 1u;
@@ -316,15 +341,20 @@ __global__ void __launch_bounds__(kThreads, A_RESIDENT ? 2 : 1) rank_topk_kernel
                     for (int i = 0; i < 8; ++i) {
                         const int ul = urow0 + 4 * i;
                         if (ul < nu) {
+                            const int64_t ar = a.row_list ? static_cast<int64_t>(a.row_list[u0 + ul]) : u0 + ul;
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 if (acc[i][j] >= tau[i])
-                                    flag |= try_append(&s_args, st, cand_cta, ul, u0 + ul, i_base + 8 * j, acc[i][j]);
+                                    flag |= try_append(&s_args, st, cand_cta, ul, ar, i_base + 8 * j, acc[i][j]);
                             }
                         }
                     }
                 }
             }
+            // the barrier of stage s finished its phase when this tile was waited for: arm it for the
+            // load that is issued right after the CTA barrier below
+            if (tid == 0 && q + 2 < Q)
+                mbar_arrive_expect_tx(s ? &bars[1] : &bars[0], stage_tx_bytes<A_RESIDENT>(a, nu, q + 2, nch));
             const int need = __syncthreads_or(flag);  // stage s fully consumed; lists complete
             if (need) {
                 uint64_t *scratch = reinterpret_cast<uint64_t *>(stage) + warp * kScratchKeys;
@@ -335,9 +365,7 @@ __global__ void __launch_bounds__(kThreads, A_RESIDENT ? 2 : 1) rank_topk_kernel
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncthreads();
             }
-            if (warp == 0 && q + 2 < Q)
-                issue_stage<A_RESIDENT>(a, stage, s ? &bars[1] : &bars[0], u0, nu, static_cast<int>((q + 2) / nch),
-                                        static_cast<int>((q + 2) % nch), lane);
+            if (q + 2 < Q) issue_stage<A_RESIDENT>(a, stage, s ? &bars[1] : &bars[0], u0, nu, q + 2, nch, tid);
         }
 
         // every issued stage has been consumed: both stages are free -> sort scratch
@@ -345,7 +373,10 @@ __global__ void __launch_bounds__(kThreads, A_RESIDENT ? 2 : 1) rank_topk_kernel
             uint64_t *scratch = reinterpret_cast<uint64_t *>(stage0) + warp * kScratchKeys;
             for (int r = 0; r < TU / kWarps; ++r) {
                 const int ul = warp * (TU / kWarps) + r;
-                if (ul < nu) finish_row(a, st, cand_cta, ul, u0 + ul, scratch, lane);
+                if (ul < nu) {
+                    const int64_t ar = a.row_list ? static_cast<int64_t>(a.row_list[u0 + ul]) : u0 + ul;
+                    finish_row(a, st, cand_cta, ul, ar, scratch, lane);
+                }
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -357,19 +388,28 @@ constexpr size_t smem_bytes(bool resident) {
     return static_cast<size_t>(resident ? 3 : 4) * kTileBytes + sizeof(RowState) + 3 * sizeof(uint64_t) + 16;
 }
 
-int rank_grid(int64_t Ma, bool resident) {
+int rank_grid(int64_t Ma, bool resident, bool listed) {
     const int64_t tiles = (Ma + TU - 1) / TU;
     const int64_t slots = static_cast<int64_t>(sm_count()) * (resident ? 2 : 1);
-    return static_cast<int>(tiles < slots ? tiles : slots);
+    return static_cast<int>((listed || tiles > slots) ? slots : tiles);
 }
 
+}  // namespace
+
 size_t rank_workspace_bytes(int64_t Ma, int d) {
+    (void)Ma;
     const bool resident = d <= KC;
     const int64_t slots = static_cast<int64_t>(sm_count()) * (resident ? 2 : 1);
     return 256 + static_cast<size_t>(slots) * TU * CAP * sizeof(uint64_t);
 }
 
-int rank_launch(RankArgs a, void *workspace, size_t workspace_bytes, cudaStream_t stm) {
+int rank_launch_engine(const EngineArgs &e, void *workspace, size_t workspace_bytes, cudaStream_t stm) {
+    RankArgs a{};
+    a.A = e.A; a.B = e.B; a.Ma = e.Ma; a.Nb = e.Nb; a.d = e.d; a.K = e.K;
+    a.mask_rowptr = e.mask_rowptr; a.mask_col = e.mask_col; a.mask_value = e.mask_value;
+    a.exclude_self = e.exclude_self; a.self_off = e.self_off; a.id_offset = e.id_offset;
+    a.out_idx = e.out_idx; a.out_score = e.out_score;
+    a.row_list = e.row_list; a.row_count_dev = e.row_count_dev;
     const bool resident = a.d <= KC;
     if (workspace_bytes < rank_workspace_bytes(a.Ma, a.d)) return CHAOREC_E_WORKSPACE;
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return CHAOREC_E_ALIGN;
@@ -379,20 +419,22 @@ int rank_launch(RankArgs a, void *workspace, size_t workspace_bytes, cudaStream_
     if (tiles > 0x7fffffffLL) return CHAOREC_E_UNSUPPORTED;
     a.n_row_tiles = static_cast<int>(tiles);
     if (cudaMemsetAsync(workspace, 0, 256, stm) != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
-    const int grid = rank_grid(a.Ma, resident);
+    const int grid = rank_grid(a.Ma, resident, a.row_list != nullptr);
     const size_t smem = smem_bytes(resident);
-    cudaError_t e;
+    cudaError_t err;
     if (resident) {
-        e = cudaFuncSetAttribute(rank_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
+        err = cudaFuncSetAttribute(rank_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (err != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
         rank_topk_kernel<true><<<grid, kThreads, smem, stm>>>(a);
     } else {
-        e = cudaFuncSetAttribute(rank_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
+        err = cudaFuncSetAttribute(rank_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (err != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
         rank_topk_kernel<false><<<grid, kThreads, smem, stm>>>(a);
     }
     return launch_status();
 }
+
+namespace {
 
 // ---- canonical row norms: sequential fp64 sum of squares, one thread per row ----------------
 __global__ void row_norm_kernel(const float *__restrict__ x, int64_t N, int D, float *__restrict__ nrm) {
@@ -441,9 +483,24 @@ size_t align256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
 
 using namespace chaorec;
 
+namespace {
+// CHAOREC_ENGINE=exact forces the fp32 CUDA-core engine (used by the tests to cover both engines).
+bool use_tensor_engine(int64_t Ma, int64_t Nb, int d, int K) {
+    const char *env = getenv("CHAOREC_ENGINE");
+    if (env && strcmp(env, "exact") == 0) return false;
+    return tc_supported(Ma, Nb, d, K);
+}
+size_t max_size(size_t a, size_t b) { return a > b ? a : b; }
+}  // namespace
+
+extern "C" int chaorec_uses_tensor_engine(int64_t rows, int64_t cols, int32_t d, int32_t K) {
+    return use_tensor_engine(rows, cols, d, K) ? 1 : 0;
+}
+
 extern "C" size_t chaorec_score_mask_topk_workspace_bytes(int64_t U, int64_t I, int32_t d, int32_t K) {
-    (void)I; (void)K;
-    return rank_workspace_bytes(U, d);
+    size_t n = rank_workspace_bytes(U, d);
+    if (tc_supported(U, I, d, K)) n = max_size(n, tc_workspace_bytes(U, I, d));
+    return n;
 }
 
 extern "C" int chaorec_score_mask_topk_f32(const float *user_emb, const float *item_emb, const int64_t *mask_rowptr,
@@ -453,15 +510,18 @@ extern "C" int chaorec_score_mask_topk_f32(const float *user_emb, const float *i
                                            void *stream) {
     if (!user_emb || !item_emb || !out_idx || U < 0 || I <= 0 || d <= 0) return CHAOREC_E_BADARG;
     if (mask_rowptr && !mask_col) return CHAOREC_E_BADARG;
-    if (K < 1 || K > kMaxK || K > I || d % 4 != 0 || I > 0xFFFFFFF0LL) return CHAOREC_E_UNSUPPORTED;
+    if (K < 1 || K > kMaxK || K > I || d % 4 != 0 || I > 0x7FFFFFF0LL || U > 0x7FFFFFF0LL) return CHAOREC_E_UNSUPPORTED;
     if (!aligned16(user_emb) || !aligned16(item_emb)) return CHAOREC_E_ALIGN;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return CHAOREC_E_ALIGN;
     if (U == 0) return CHAOREC_OK;
-    RankArgs a{};
-    a.A = user_emb; a.B = item_emb; a.Ma = U; a.Nb = I; a.d = d; a.K = K;
-    a.mask_rowptr = mask_rowptr; a.mask_col = mask_col; a.mask_value = mask_value;
-    a.exclude_self = 0; a.self_off = 0; a.id_offset = id_offset;
-    a.out_idx = out_idx; a.out_score = out_score;
-    return rank_launch(a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    EngineArgs e{};
+    e.A = user_emb; e.B = item_emb; e.Ma = U; e.Nb = I; e.d = d; e.K = K;
+    e.mask_rowptr = mask_rowptr; e.mask_col = mask_col; e.mask_value = mask_value;
+    e.exclude_self = 0; e.self_off = 0; e.id_offset = id_offset;
+    e.out_idx = out_idx; e.out_score = out_score;
+    cudaStream_t stm = static_cast<cudaStream_t>(stream);
+    if (use_tensor_engine(U, I, d, K)) return tc_topk_launch(e, workspace, workspace_bytes, stm);
+    return rank_launch_engine(e, workspace, workspace_bytes, stm);
 }
 
 extern "C" int chaorec_l2_normalize_f32(const float *x, int64_t N, int32_t D, float *out, float *norms,
@@ -474,9 +534,9 @@ extern "C" int chaorec_l2_normalize_f32(const float *x, int64_t N, int32_t D, fl
 }
 
 extern "C" size_t chaorec_knn_workspace_bytes(int64_t N, int32_t D, int32_t k) {
-    (void)k;
-    return align256(static_cast<size_t>(N) * D * sizeof(float)) + align256(static_cast<size_t>(N) * sizeof(float)) +
-           rank_workspace_bytes(N, D);
+    size_t n = rank_workspace_bytes(N, D);
+    if (tc_supported(N, N, D, k)) n = max_size(n, tc_workspace_bytes(N, N, D));
+    return align256(static_cast<size_t>(N) * D * sizeof(float)) + align256(static_cast<size_t>(N) * sizeof(float)) + n;
 }
 
 extern "C" int chaorec_knn_cosine_topk(const float *feats, int64_t N, int32_t D, int32_t k, int exclude_self,
@@ -484,7 +544,7 @@ extern "C" int chaorec_knn_cosine_topk(const float *feats, int64_t N, int32_t D,
                                        void *workspace, size_t workspace_bytes, void *stream) {
     if (!feats || !out_val || !out_idx || N <= 0 || D <= 0 || row_lo < 0 || row_hi > N || row_lo > row_hi)
         return CHAOREC_E_BADARG;
-    if (k < 1 || k > kMaxK || k > N - (exclude_self ? 1 : 0) || D % 4 != 0 || N > 0xFFFFFFF0LL)
+    if (k < 1 || k > kMaxK || k > N - (exclude_self ? 1 : 0) || D % 4 != 0 || N > 0x7FFFFFF0LL)
         return CHAOREC_E_UNSUPPORTED;
     if (!aligned16(feats)) return CHAOREC_E_ALIGN;
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return CHAOREC_E_ALIGN;
@@ -498,11 +558,12 @@ extern "C" int chaorec_knn_cosine_topk(const float *feats, int64_t N, int32_t D,
     ws += align256(static_cast<size_t>(N) * sizeof(float));
     int rc = normalize_launch(feats, N, D, cn, nrm, stm);
     if (rc != CHAOREC_OK) return rc;
-    RankArgs a{};
-    a.A = cn + row_lo * D; a.B = cn; a.Ma = row_hi - row_lo; a.Nb = N; a.d = D; a.K = k;
-    a.mask_rowptr = nullptr; a.mask_col = nullptr; a.mask_value = 0.0f;
-    a.exclude_self = exclude_self ? 1 : 0; a.self_off = row_lo; a.id_offset = 0;
-    a.out_idx = out_idx; a.out_score = out_val;
-    return rank_launch(a, ws, workspace_bytes - static_cast<size_t>(ws - reinterpret_cast<unsigned char *>(workspace)),
-                       stm);
+    EngineArgs e{};
+    e.A = cn + row_lo * D; e.B = cn; e.Ma = row_hi - row_lo; e.Nb = N; e.d = D; e.K = k;
+    e.mask_rowptr = nullptr; e.mask_col = nullptr; e.mask_value = 0.0f;
+    e.exclude_self = exclude_self ? 1 : 0; e.self_off = row_lo; e.id_offset = 0;
+    e.out_idx = out_idx; e.out_score = out_val;
+    const size_t left = workspace_bytes - static_cast<size_t>(ws - reinterpret_cast<unsigned char *>(workspace));
+    if (use_tensor_engine(e.Ma, N, D, k)) return tc_topk_launch(e, ws, left, stm);
+    return rank_launch_engine(e, ws, left, stm);
 }

@@ -1,0 +1,622 @@
+// K3 / K2 pre-filter: bf16 tcgen05 tensor-core dot products with a fused threshold/top-K' epilogue.
+//
+// For every row of A (users, or L2-normalised item features) the kernel finds the K' columns of B
+// with the largest APPROXIMATE dot product (bf16 operands, fp32 accumulation in TMEM) without
+// ever writing a score to memory.  The approximate winners are then re-scored in exact canonical
+// fp32 (rescore kernel below) and the exact top-K is certified with a rigorous error bound; rows
+// that cannot be certified are re-run by the exact CUDA-core engine (rank_topk.cu).  This is the
+// "bf16 tcgen05 cosine-similarity GEMM ... candidates re-scored in fp32 before top-k" of
+// north_star, shared by the kNN builders (Model/FREEDOM.py:114-118) and gene_ranklist
+// (Model/LightGCN.py:147-155).
+//
+// Kernel anatomy (one persistent CTA per SM, 320 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d loads of a [256 x 64] bf16 slab of A and a
+//               [128 x 64] slab of B per pipeline stage (128-byte swizzle, 3-stage mbarrier ring)
+//   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma
+//               (cta_group::1, kind::f16, M=128, N=128, K=16) for the two 128-row halves of the
+//               A slab; accumulators live in TMEM (2 halves x 2 stages x 128 columns = 512 cols);
+//               tcgen05.commit releases smem stages and publishes finished accumulators
+//   warps 2-9   epilogue: thread <-> one row of the 256-row tile (TMEM lane), tcgen05.ld
+//               32x32b.x32 chunks, one FSETP per score against the row's running threshold, the
+//               rare survivors are appended to a thread-private candidate list (L2-resident
+//               workspace); when a list fills, the warp sorts it in shared memory, keeps the best
+//               K' and raises the threshold
+// Work unit = (256-row tile of A, column slice of B); units are dealt round-robin to CTAs.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "engine.cuh"
+
+namespace chaorec {
+namespace {
+
+constexpr int BM = 256;          // rows of A per unit (two MMA halves of 128)
+constexpr int BN = 128;          // columns per accumulator tile
+constexpr int BK = 64;           // bf16 elements per pipeline stage (= one 128-byte swizzle row)
+constexpr int kStages = 3;
+constexpr int kABytes = BM * BK * 2;   // 32 KB
+constexpr int kBBytes = BN * BK * 2;   // 16 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kTcThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr int TC_CAP = 1024;     // candidate slots per row inside a unit
+constexpr int kTcTrigger = TC_CAP - BN;
+constexpr int KP_MAX = 128;      // K' (approximate candidates kept per (row, slice)) is 64 or 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO=1024 B, version 1, SWIZZLE_128B
+
+struct TcArgs {
+    int64_t Ma, Nb;
+    int D;
+    int n_row_tiles, n_slices, tiles_per_slice;   // tiles = BN-column tiles
+    int kp;                                        // K': candidates kept per (row, slice)
+    const int64_t *mask_rowptr;
+    const int32_t *mask_col;
+    int exclude_self;
+    int64_t self_off;
+    uint64_t *cand_ws;        // [gridDim.x][BM][TC_CAP]
+    uint64_t *cand_out;       // [Ma][n_slices][KP] approximate keys, best first (0 = empty)
+    float *tprime_out;        // [Ma][n_slices] approx score of the KP-th kept candidate (-inf: list complete)
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t smem_desc(const void *p) {
+    return (static_cast<uint64_t>(kDescHi) << 32) | static_cast<uint64_t>((smem_u32(p) >> 4) & 0x3FFFu);
+}
+
+// ---- epilogue helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ void warp_sort_desc_tc(uint64_t *s, int P, int lane) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (P >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool desc = ((i & k) == 0);
+                const uint64_t a = s[i], b = s[l];
+                if ((a < b) == desc && a != b) {
+                    s[i] = b;
+                    s[l] = a;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// rare path: a score passed the row threshold
+__device__ __noinline__ int tc_append(const TcArgs *__restrict__ a, uint64_t *row_buf, int cnt, int64_t row, int64_t col,
+                                      float s) {
+    if (col >= a->Nb) return cnt;                                  // zero-filled out-of-range column
+    if (a->exclude_self && col == row + a->self_off) return cnt;
+    if (a->mask_rowptr != nullptr) {                               // train items re-enter later at mask_value
+        int64_t lo = a->mask_rowptr[row], hi = a->mask_rowptr[row + 1];
+        const int32_t want = static_cast<int32_t>(col);
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            const int32_t v = a->mask_col[mid];
+            if (v == want) return cnt;
+            if (v < want) lo = mid + 1; else hi = mid;
+        }
+    }
+    if (cnt < TC_CAP) row_buf[cnt] = make_key(s, static_cast<uint32_t>(col));
+    return cnt + 1;
+}
+
+// The warp sorts the list of lane `src`'s row and keeps the best KP; returns (new count, new tau)
+// to every lane (only lane `src` uses them).
+__device__ __forceinline__ void tc_merge(uint64_t *row_buf_src, int n, uint64_t *scratch, int lane, int KP, int &new_cnt,
+                                         float &new_tau) {
+    if (n > TC_CAP) n = TC_CAP;
+    int P = 64;
+    while (P < n) P <<= 1;
+    for (int t = lane; t < P; t += 32) scratch[t] = (t < n) ? row_buf_src[t] : 0ull;
+    __syncwarp();
+    warp_sort_desc_tc(scratch, P, lane);
+    const int keep = n < KP ? n : KP;
+    for (int t = lane; t < keep; t += 32) row_buf_src[t] = scratch[t];
+    new_cnt = keep;
+    new_tau = (n >= KP) ? key_score(scratch[KP - 1]) : -INFINITY;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcArgs a) {
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    // layout: [stage 0..2: A slab | B slab] [sort scratch 8 x 8 KB] [barriers] [tmem base] [args]
+    unsigned char *stages = tc_smem;
+    uint64_t *scratch_all = reinterpret_cast<uint64_t *>(tc_smem + kStages * kStageBytes);
+    uint64_t *bars = scratch_all + kEpiWarps * TC_CAP;
+    uint64_t *full_bar = bars;                    // [kStages]
+    uint64_t *empty_bar = bars + kStages;         // [kStages]
+    uint64_t *tfull_bar = bars + 2 * kStages;     // [2]
+    uint64_t *tempty_bar = bars + 2 * kStages + 2;  // [2]
+    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+    TcArgs *s_args = reinterpret_cast<TcArgs *>(tmem_base_smem + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        *s_args = a;
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], kEpiWarps * 32);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_base_smem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    const int n_units = a.n_row_tiles * a.n_slices;
+    const int n_kc = (a.D + BK - 1) / BK;
+    const int n_col_tiles = static_cast<int>((a.Nb + BN - 1) / BN);
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                const int rt = unit / a.n_slices, sl = unit % a.n_slices;
+                const int t_lo = sl * a.tiles_per_slice;
+                const int t_hi = min(t_lo + a.tiles_per_slice, n_col_tiles);
+                for (int t = t_lo; t < t_hi; ++t) {
+                    for (int kc = 0; kc < n_kc; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        unsigned char *sa = stages + stage * kStageBytes;
+                        mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                        tma_load_2d(sa, &map_a, kc * BK, rt * BM, &full_bar[stage]);
+                        tma_load_2d(sa + kABytes, &map_b, kc * BK, t * BN, &full_bar[stage]);
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                const int sl = unit % a.n_slices;
+                const int t_lo = sl * a.tiles_per_slice;
+                const int t_hi = min(t_lo + a.tiles_per_slice, n_col_tiles);
+                for (int t = t_lo; t < t_hi; ++t) {
+                    mbar_wait(&tempty_bar[as], aphase ^ 1u);      // epilogue drained this accumulator stage
+                    tc_fence_after();
+                    for (int kc = 0; kc < n_kc; ++kc) {
+                        mbar_wait(&full_bar[stage], phase);       // TMA bytes have landed
+                        tc_fence_after();
+                        const unsigned char *sa = stages + stage * kStageBytes;
+                        const uint64_t da0 = smem_desc(sa);
+                        const uint64_t da1 = smem_desc(sa + 128 * BK * 2);
+                        const uint64_t db = smem_desc(sa + kABytes);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint32_t acc = (kc > 0 || k > 0) ? 1u : 0u;
+                            // +32 bytes along K inside the 128-byte swizzle row = +2 in the (>>4) address field
+                            umma_bf16(tmem_base + (as * 2 + 0) * BN, da0 + 2 * k, db + 2 * k, kIdesc, acc);
+                            umma_bf16(tmem_base + (as * 2 + 1) * BN, da1 + 2 * k, db + 2 * k, kIdesc, acc);
+                        }
+                        umma_commit(&empty_bar[stage]);           // smem stage reusable once these MMAs retire
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit(&tfull_bar[as]);                  // accumulators complete
+                    if (++as == 2) { as = 0; aphase ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ================= epilogue: one thread per row =================
+        const int ew = warp - 2;                 // 0..7
+        const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+        const int h = ew >> 2;                   // which 128-row half
+        const int row_local = h * 128 + q * 32 + lane;
+        uint64_t *scratch = scratch_all + ew * TC_CAP;
+        uint64_t *row_buf = a.cand_ws + (static_cast<size_t>(blockIdx.x) * BM + row_local) * TC_CAP;
+        int as = 0;
+        uint32_t aphase = 0;
+        const int KP = a.kp;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int rt = unit / a.n_slices, sl = unit % a.n_slices;
+            const int t_lo = sl * a.tiles_per_slice;
+            const int t_hi = min(t_lo + a.tiles_per_slice, n_col_tiles);
+            const int64_t row = static_cast<int64_t>(rt) * BM + row_local;
+            const bool row_ok = row < a.Ma;
+            float tau = row_ok ? -INFINITY : INFINITY;
+            int cnt = 0;
+            for (int t = t_lo; t < t_hi; ++t) {
+                mbar_wait(&tfull_bar[as], aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * 2 + h) * BN;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    __syncwarp();
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    bool any = false;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) any |= (__uint_as_float(v[j]) > tau);
+                    if (any) {
+                        const int64_t col0 = static_cast<int64_t>(t) * BN + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float s = __uint_as_float(v[j]);
+                            if (s > tau) cnt = tc_append(s_args, row_buf, cnt, row, col0 + j, s);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[as]);                     // this thread is done with the stage
+                if (++as == 2) { as = 0; aphase ^= 1u; }
+                // lists that could overflow during the next tile are compacted now (warp-cooperative)
+                __syncwarp();                                     // appended keys visible to the whole warp
+                unsigned need = __ballot_sync(0xffffffffu, cnt > kTcTrigger);
+                while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int n_src = __shfl_sync(0xffffffffu, cnt, src);
+                    uint64_t *buf_src = a.cand_ws + (static_cast<size_t>(blockIdx.x) * BM + (row_local - lane + src)) * TC_CAP;
+                    int nc;
+                    float nt;
+                    tc_merge(buf_src, n_src, scratch, lane, KP, nc, nt);
+                    if (lane == src) { cnt = nc; tau = nt; }
+                }
+            }
+            // ---- end of unit: sort every row's list, publish the best KP and the cut-off t' ----
+            __syncwarp();
+            for (int src = 0; src < 32; ++src) {
+                const int n_src = __shfl_sync(0xffffffffu, cnt, src);
+                const float tau_src = __shfl_sync(0xffffffffu, tau, src);
+                const int64_t row_src = row - lane + src;
+                if (row_src >= a.Ma) continue;                    // warp-uniform
+                uint64_t *buf_src = a.cand_ws + (static_cast<size_t>(blockIdx.x) * BM + (row_local - lane + src)) * TC_CAP;
+                int nc;
+                float nt;
+                tc_merge(buf_src, n_src, scratch, lane, KP, nc, nt);
+                // after tc_merge scratch[0..P) is sorted; entries beyond nc are ignored
+                uint64_t *out = a.cand_out + (static_cast<size_t>(row_src) * a.n_slices + sl) * KP;
+                for (int t2 = lane; t2 < KP; t2 += 32) out[t2] = (t2 < nc) ? scratch[t2] : 0ull;
+                if (lane == 0) {
+                    // columns never appended scored <= the threshold in force when they were seen, and
+                    // every threshold is <= the final KP-th best; a list that never filled is complete
+                    const float tp = (n_src >= KP) ? nt : tau_src;
+                    a.tprime_out[static_cast<size_t>(row_src) * a.n_slices + sl] = tp;
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+constexpr size_t tc_smem_bytes() {
+    return static_cast<size_t>(kStages) * kStageBytes + static_cast<size_t>(kEpiWarps) * TC_CAP * 8 + (2 * kStages + 4) * 8 + 16 +
+           sizeof(TcArgs) + 64;
+}
+
+// ---- fp32 -> bf16 operand copies (+ row norms for the error bound) ------------------------------
+__global__ void to_bf16_kernel(const float *__restrict__ x, int64_t n_rows, int D, __nv_bfloat16 *__restrict__ out,
+                               float *__restrict__ row_norm) {
+    // one warp per row: bf16 (round-to-nearest-even) copy and the fp32 L2 norm of the row
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    float ss = 0.0f;
+    for (int k = lane * 4; k < D; k += 128) {
+        const float4 v = *reinterpret_cast<const float4 *>(x + row * D + k);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<__nv_bfloat162 *>(out + row * D + k) = lo;
+        *reinterpret_cast<__nv_bfloat162 *>(out + row * D + k + 2) = hi;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    // rounded up (fp32 summation error <= D*2^-24 relative): the norm feeds an upper bound
+    if (lane == 0 && row_norm) row_norm[row] = sqrtf(ss) * (1.0f + 2.0e-7f * static_cast<float>(D));
+}
+
+__global__ void max_reduce_kernel(const float *__restrict__ x, int64_t n, float *__restrict__ out) {
+    // single block; out[0] = max(x)
+    __shared__ float sm[32];
+    float m = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, x[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) out[0] = m;
+    }
+}
+
+// ---- exact re-score + certification ---------------------------------------------------------------
+struct RescoreArgs {
+    const float *A;            // fp32 operands (canonical arithmetic)
+    const float *B;
+    int64_t Ma, Nb;
+    int D, K, n_slices, kp;
+    const uint64_t *cand;      // [Ma][n_slices][kp]
+    const float *tprime;       // [Ma][n_slices]
+    const float *a_norm;       // [Ma] (upper bounds of the fp32 row norms)
+    const float *b_norm_max;   // [1]
+    float gamma;               // relative error bound of an approximate score: |s~ - s| <= gamma*|a|*|b|max
+    const int64_t *mask_rowptr;
+    const int32_t *mask_col;
+    float mask_value;
+    int64_t id_offset;
+    int64_t *out_idx;
+    float *out_score;
+    int32_t *fallback_rows;    // rows whose exact top-K could not be certified
+    unsigned int *fallback_count;
+};
+
+constexpr int kRescoreMax = 1024;  // n_slices * kp + K masked (<= 4*128 + 64), padded to a power of two
+constexpr int kRescoreWarps = 4;
+
+// one warp per row
+__global__ void __launch_bounds__(kRescoreWarps * 32) rescore_kernel(const RescoreArgs a) {
+    __shared__ uint64_t keys_all[kRescoreWarps][kRescoreMax];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * kRescoreWarps + wib;
+    if (row >= a.Ma) return;
+    uint64_t *keys = keys_all[wib];
+    const int n_in = a.n_slices * a.kp;
+    const float *ar = a.A + row * a.D;
+    float tmax = -INFINITY;
+    for (int s = lane; s < a.n_slices; s += 32) tmax = fmaxf(tmax, a.tprime[row * a.n_slices + s]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    int nm = 0;
+    int64_t m_lo = 0;
+    if (a.mask_rowptr != nullptr) {
+        m_lo = a.mask_rowptr[row];
+        const int64_t len = a.mask_rowptr[row + 1] - m_lo;
+        nm = len < a.K ? static_cast<int>(len) : a.K;
+    }
+    int P = 64;
+    while (P < n_in + nm) P <<= 1;
+    for (int t = lane; t < P; t += 32) {
+        uint64_t key = 0ull;
+        if (t < n_in) {
+            const uint64_t ak = a.cand[static_cast<size_t>(row) * n_in + t];
+            if (ak != 0ull) {
+                const uint32_t col = key_index(ak);
+                const float *br = a.B + static_cast<int64_t>(col) * a.D;
+                float acc = 0.0f;
+                for (int k = 0; k < a.D; k += 4) {            // canonical chain: k ascending, one fmaf per term
+                    const float4 x = *reinterpret_cast<const float4 *>(ar + k);
+                    const float4 y = __ldg(reinterpret_cast<const float4 *>(br + k));
+                    acc = fmaf(x.x, y.x, acc);
+                    acc = fmaf(x.y, y.y, acc);
+                    acc = fmaf(x.z, y.z, acc);
+                    acc = fmaf(x.w, y.w, acc);
+                }
+                key = make_key(acc, col);
+            }
+        } else if (t < n_in + nm) {
+            const int32_t m = a.mask_col[m_lo + (t - n_in)];
+            if (m >= 0 && m < a.Nb) key = make_key(a.mask_value, static_cast<uint32_t>(m));
+        }
+        keys[t] = key;
+    }
+    __syncwarp();
+    warp_sort_desc_tc(keys, P, lane);
+    // certification: every column outside the candidate lists has approximate score <= tmax, hence
+    // exact score <= tmax + eps; the exact top-K is final iff its K-th score is strictly above that.
+    const uint64_t kth = keys[a.K - 1];
+    const float eps = a.gamma * a.a_norm[row] * a.b_norm_max[0];
+    const bool complete = (tmax == -INFINITY);
+    const bool ok = kth != 0ull && (complete || key_score(kth) > tmax + eps);
+    if (ok) {
+        for (int t = lane; t < a.K; t += 32) {
+            const uint64_t key = keys[t];
+            a.out_idx[row * a.K + t] = static_cast<int64_t>(key_index(key)) + a.id_offset;
+            if (a.out_score) a.out_score[row * a.K + t] = key_score(key);
+        }
+    } else if (lane == 0) {
+        const unsigned slot = atomicAdd(a.fallback_count, 1u);
+        a.fallback_rows[slot] = static_cast<int32_t>(row);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+bool make_map(CUtensorMap *map, const void *base, int64_t rows, int D, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(D) * 2};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t al256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+// Host orchestration shared by the eval and kNN entry points.
+// -------------------------------------------------------------------------------------------------
+int tc_choose_slices(int64_t Ma, int64_t Nb) {
+    const int row_tiles = static_cast<int>((Ma + BM - 1) / BM);
+    const int col_tiles = static_cast<int>((Nb + BN - 1) / BN);
+    const int sms = sm_count();
+    int slices = 1;
+    // enough units to balance the persistent grid (>= 4 waves of work items), at most 4 slices so
+    // that n_slices*KP + K candidates fit the re-score buffer
+    while (slices < 4 && row_tiles * slices < 4 * sms && col_tiles / (slices * 2) >= 8) slices *= 2;
+    return slices;
+}
+
+size_t tc_workspace_bytes(int64_t Ma, int64_t Nb, int D) {
+    const int slices = tc_choose_slices(Ma, Nb);
+    size_t n = 256;                                                    // counters
+    n += al256(static_cast<size_t>(Ma) * D * 2);                        // A bf16
+    n += al256(static_cast<size_t>(Nb) * D * 2);                        // B bf16
+    n += al256(static_cast<size_t>(Ma) * 4) + al256(static_cast<size_t>(Nb) * 4) + 256;   // norms, max
+    n += al256(static_cast<size_t>(sm_count()) * BM * TC_CAP * 8);      // per-CTA candidate lists
+    n += al256(static_cast<size_t>(Ma) * slices * KP_MAX * 8);          // published candidates
+    n += al256(static_cast<size_t>(Ma) * slices * 4);                   // t'
+    n += al256(static_cast<size_t>(Ma) * 4);                            // fallback row list
+    n += rank_workspace_bytes(Ma, D);                                   // exact engine for uncertified rows
+    return n;
+}
+
+bool tc_supported(int64_t Ma, int64_t Nb, int D, int K) {
+    // small problems stay on the exact engine (nothing to win, and K' must be well below Nb)
+    return D % 8 == 0 && D >= 8 && K >= 1 && K <= 64 && Nb >= 8 * BN && Ma >= 1 && Ma < 0x7FFFFFF0LL && encode_fn() != nullptr;
+}
+
+// A, B: fp32 operands (same pointer allowed).  Computes exact canonical top-K of every row of A.
+int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes, cudaStream_t stm) {
+    if (workspace_bytes < tc_workspace_bytes(e.Ma, e.Nb, e.d)) return CHAOREC_E_WORKSPACE;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    unsigned int *counters = reinterpret_cast<unsigned int *>(ws); ws += 256;
+    __nv_bfloat16 *a16 = reinterpret_cast<__nv_bfloat16 *>(ws); ws += al256(static_cast<size_t>(e.Ma) * e.d * 2);
+    __nv_bfloat16 *b16 = reinterpret_cast<__nv_bfloat16 *>(ws); ws += al256(static_cast<size_t>(e.Nb) * e.d * 2);
+    float *a_norm = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
+    float *b_norm = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Nb) * 4);
+    float *b_max = reinterpret_cast<float *>(ws); ws += 256;
+    uint64_t *cand_ws = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(sm_count()) * BM * TC_CAP * 8);
+    const int slices = tc_choose_slices(e.Ma, e.Nb);
+    uint64_t *cand_out = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * KP_MAX * 8);
+    const int kp = e.K <= 24 ? 64 : 128;
+    float *tprime = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * 4);
+    int32_t *fb_rows = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
+    void *rank_ws = ws;
+    const size_t rank_ws_bytes = workspace_bytes - static_cast<size_t>(ws - static_cast<unsigned char *>(workspace));
+
+    if (cudaMemsetAsync(counters, 0, 256, stm) != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
+    {
+        const int wpb = 8;
+        to_bf16_kernel<<<static_cast<unsigned>((e.Ma + wpb - 1) / wpb), wpb * 32, 0, stm>>>(e.A, e.Ma, e.d, a16, a_norm);
+        to_bf16_kernel<<<static_cast<unsigned>((e.Nb + wpb - 1) / wpb), wpb * 32, 0, stm>>>(e.B, e.Nb, e.d, b16, b_norm);
+        max_reduce_kernel<<<1, 1024, 0, stm>>>(b_norm, e.Nb, b_max);
+    }
+    CUtensorMap map_a, map_b;
+    if (!make_map(&map_a, a16, e.Ma, e.d, BM) || !make_map(&map_b, b16, e.Nb, e.d, BN)) return CHAOREC_E_LAUNCH;
+
+    TcArgs t{};
+    t.Ma = e.Ma; t.Nb = e.Nb; t.D = e.d;
+    t.n_row_tiles = static_cast<int>((e.Ma + BM - 1) / BM);
+    t.n_slices = slices;
+    const int col_tiles = static_cast<int>((e.Nb + BN - 1) / BN);
+    t.tiles_per_slice = (col_tiles + slices - 1) / slices;
+    t.mask_rowptr = e.mask_rowptr; t.mask_col = e.mask_col;
+    t.exclude_self = e.exclude_self; t.self_off = e.self_off;
+    t.cand_ws = cand_ws; t.cand_out = cand_out; t.tprime_out = tprime; t.kp = kp;
+    const int n_units = t.n_row_tiles * slices;
+    const int grid = n_units < sm_count() ? n_units : sm_count();
+    const size_t smem = tc_smem_bytes();
+    if (cudaFuncSetAttribute(tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
+        cudaSuccess) {
+        cudaGetLastError();
+        return CHAOREC_E_LAUNCH;
+    }
+    tc_candidates_kernel<<<grid, kTcThreads, smem, stm>>>(map_a, map_b, t);
+
+    RescoreArgs r{};
+    r.A = e.A; r.B = e.B; r.Ma = e.Ma; r.Nb = e.Nb; r.D = e.d; r.K = e.K; r.n_slices = slices; r.kp = kp;
+    r.cand = cand_out; r.tprime = tprime; r.a_norm = a_norm; r.b_norm_max = b_max;
+    // |bf16(x)-x| <= 2^-9|x| per operand -> products within (2^-8 + 2^-18) relative; tensor-core fp32
+    // accumulation (assumed no worse than truncation per add) and the canonical chain's own rounding
+    // add at most 3*D*2^-24 relative to sum|a_k b_k| <= |a||b|.
+    r.gamma = 0.00390625f * 1.01f + 3.0f * static_cast<float>(e.d) * 5.9604645e-8f;
+    r.mask_rowptr = e.mask_rowptr; r.mask_col = e.mask_col; r.mask_value = e.mask_value;
+    r.id_offset = e.id_offset; r.out_idx = e.out_idx; r.out_score = e.out_score;
+    r.fallback_rows = fb_rows; r.fallback_count = counters + 16;
+    rescore_kernel<<<static_cast<unsigned>((e.Ma + kRescoreWarps - 1) / kRescoreWarps), kRescoreWarps * 32, 0, stm>>>(r);
+    int rc = launch_status();
+    if (rc != CHAOREC_OK) return rc;
+    // rows that could not be certified: exact CUDA-core engine over the listed rows only
+    EngineArgs fb = e;
+    fb.row_list = fb_rows;
+    fb.row_count_dev = counters + 16;
+    return rank_launch_engine(fb, rank_ws, rank_ws_bytes, stm);
+}
+
+}  // namespace chaorec

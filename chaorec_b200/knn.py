@@ -20,7 +20,7 @@ from . import _lib
 
 
 def knn_topk(feats: torch.Tensor, k: int, exclude_self: bool = False,
-             row_range: Optional[Tuple[int, int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+             row_range: Optional[Tuple[int, int]] = None, stats: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Cosine top-k of every row (or of rows [lo, hi)) against all rows.
 
     Returns (val float32 [n, k] descending, idx int64 [n, k]); ties -> ascending column.
@@ -39,6 +39,11 @@ def knn_topk(feats: torch.Tensor, k: int, exclude_self: bool = False,
                                          _lib.ptr(out_val), _lib.ptr(out_idx), _lib.ptr(ws), ws.numel(),
                                          _lib.stream_ptr(dev))
     _lib.check(rc, "chaorec_knn_cosine_topk")
+    if stats is not None:
+        tensor = bool(lib.chaorec_uses_tensor_engine(hi - lo, N, D, int(k)))
+        stats["engine"] = "tensor" if tensor else "exact"
+        off = ((N * D * 4 + 255) // 256) * 256 + ((N * 4 + 255) // 256) * 256 + 64   # normalised rows, norms, counters
+        stats["fallback_rows"] = int(ws[off:off + 4].view(torch.int32).item()) if tensor else 0
     return out_val, out_idx
 
 

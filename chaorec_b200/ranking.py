@@ -66,8 +66,11 @@ def mask_csr_from_edges(users: torch.Tensor, local_items: torch.Tensor, num_user
 
 
 def rank_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, mask: Optional[MaskCSR], topk: int,
-              mask_value: float = 1e-6, id_offset: int = 0, return_scores: bool = False):
-    """Fused score -> mask -> top-K.  Returns int64 [U, topk] (and float32 scores)."""
+              mask_value: float = 1e-6, id_offset: int = 0, return_scores: bool = False, stats: Optional[dict] = None):
+    """Fused score -> mask -> top-K.  Returns int64 [U, topk] (and float32 scores).
+
+    ``stats`` (optional dict) receives ``engine`` ('tensor' | 'exact') and, for the tensor engine,
+    ``fallback_rows`` = rows re-run by the exact engine (reading it synchronises the stream)."""
     _lib.require_cuda(user_emb, "user_emb")
     _lib.require_cuda(item_emb, "item_emb")
     lib = _lib.load()
@@ -87,6 +90,10 @@ def rank_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, mask: Optional[Mas
             _lib.ptr(mask.col) if mask else None, float(np.float32(mask_value)), U, I, d, int(topk),
             int(id_offset), _lib.ptr(out_idx), _lib.ptr(out_score), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
     _lib.check(rc, "chaorec_score_mask_topk_f32")
+    if stats is not None:
+        tensor = bool(lib.chaorec_uses_tensor_engine(U, I, d, int(topk)))
+        stats["engine"] = "tensor" if tensor else "exact"
+        stats["fallback_rows"] = int(ws[64:68].view(torch.int32).item()) if tensor else 0
     return (out_idx, out_score) if return_scores else out_idx
 
 

@@ -107,6 +107,19 @@ int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float 
  * mask_rowptr == NULL => nothing masked.
  */
 size_t chaorec_score_mask_topk_workspace_bytes(int64_t U, int64_t I, int32_t d, int32_t K);
+
+/*
+ * Two engines compute the same canonical result:
+ *   exact   fp32 CUDA cores, every score is the canonical chain (csrc/rank_topk.cu);
+ *   tensor  bf16 tcgen05 pre-filter keeps the K' best approximate columns per row, those are
+ *           re-scored with the canonical chain and the exact top-K is certified with a rigorous
+ *           error bound; uncertified rows are re-run by the exact engine (csrc/tc_candidates.cu).
+ * Returns 1 when the tensor engine will be used for this shape (d % 8 == 0, >= 1024 columns; the
+ * environment variable CHAOREC_ENGINE=exact forces the exact engine), else 0.  When it is used,
+ * the uint32 at byte offset 64 of the workspace holds the number of rows that were re-run by the
+ * exact engine once the call has completed.
+ */
+int chaorec_uses_tensor_engine(int64_t rows, int64_t cols, int32_t d, int32_t K);
 int chaorec_score_mask_topk_f32(const float *user_emb, const float *item_emb, const int64_t *mask_rowptr,
                                 const int32_t *mask_col, float mask_value, int64_t U, int64_t I, int32_t d,
                                 int32_t K, int64_t id_offset, int64_t *out_idx, float *out_score,

@@ -66,3 +66,14 @@ def metrics_array(m, ks):
 def canon():
     from oracle.canon_py import Canon
     return Canon()
+
+
+@pytest.fixture(params=["auto", "exact"])
+def engine(request, monkeypatch):
+    """Runs a test once per top-K engine: 'auto' = the bf16 tcgen05 pre-filter + exact re-score where
+    the shape allows it (d % 8 == 0, >= 1024 columns), 'exact' = the fp32 CUDA-core engine everywhere."""
+    if request.param == "exact":
+        monkeypatch.setenv("CHAOREC_ENGINE", "exact")
+    else:
+        monkeypatch.delenv("CHAOREC_ENGINE", raising=False)
+    return request.param

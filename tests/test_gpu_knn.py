@@ -10,7 +10,7 @@ import chaorec_b200 as cb
 from conftest import load_golden
 from oracle import ref_ops
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("engine")]
 
 
 def dev():

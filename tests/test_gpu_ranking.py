@@ -13,7 +13,7 @@ import chaorec_b200 as cb
 from conftest import dict_from_train, load_golden, metrics_array, rows_to_object_array, unflatten_rows
 from oracle import ref_ops
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("engine")]
 
 
 def dev():
@@ -195,3 +195,28 @@ def test_million_user_config_sampled_bit_exact(canon):
     cidx, csc = canon.score_mask_topk(u[sample].numpy(), it.numpy(), sub_rp, np.concatenate(cols), 1e-6, K, id_offset=U)
     assert np.array_equal(idx[sample.to(dev())].cpu().numpy(), cidx)
     assert np.array_equal(sc[sample.to(dev())].cpu().numpy().view(np.uint32), csc.view(np.uint32))
+
+
+def test_tensor_engine_is_used_and_rarely_falls_back(canon, engine):
+    """The tcgen05 pre-filter must actually run for the big shapes, certify almost every row, and
+    hand the rest to the exact engine (results are bit-exact either way)."""
+    U, I, d, K = 5000, 6000, 64, 20
+    u = ref_ops.normal_embeddings(U, d, 71)
+    it = ref_ops.normal_embeddings(I, d, 72)
+    tu, ti = ref_ops.synth_interactions(U, I, 8 * U, 73)
+    mask = cb.mask_csr_from_edges(tu.to(dev()), ti.to(dev()), U, I)
+    stats = {}
+    idx = cb.rank_topk(u.to(dev()), it.to(dev()), mask, K, 1e-6, 0, stats=stats)
+    assert stats["engine"] == ("tensor" if engine == "auto" else "exact")
+    rp, col = _csr_np(mask)
+    cidx, _ = canon.score_mask_topk(u.numpy(), it.numpy(), rp, col, 1e-6, K, 0)
+    assert np.array_equal(idx.cpu().numpy(), cidx)
+    if engine == "auto":
+        assert stats["fallback_rows"] <= U // 20
+    # adversarial for the pre-filter: 300 near-duplicate items within bf16 resolution of each other
+    it2 = it.clone()
+    it2[1000:1300] = it[5] * (1.0 + 1e-4 * torch.arange(300).float().unsqueeze(1))
+    stats = {}
+    idx = cb.rank_topk(u.to(dev()), it2.to(dev()), None, K, 1e-6, 0, stats=stats)
+    cidx, _ = canon.score_mask_topk(u.numpy(), it2.numpy(), None, None, 1e-6, K, 0)
+    assert np.array_equal(idx.cpu().numpy(), cidx)
