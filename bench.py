@@ -194,6 +194,9 @@ def run_eval_leg(args, dev, rank, world, peaks):
     hits = torch.empty(n_local, dtype=torch.int64, device=dev)
     l2buf = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
+    st = {}
+    cb.rank_topk(ue, ie, mask, K, 1e-6, U, stats=st)            # which engine, how many rows fell back
+
     def one_step(timed):
         flush_l2(l2buf)
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -251,16 +254,26 @@ def run_eval_leg(args, dev, rank, world, peaks):
     fp32_peak = probe_fp32_peak(dev)
     flops = 2.0 * n_local * I * d
     achieved = flops / t_rank_kernel / 1e12
+    tensor = st.get("engine") == "tensor"
+    if tensor:
+        roof = dict(kernel="tc_candidates_kernel (tcgen05 bf16 pre-filter; time includes bf16 conversion, fp32 re-score + "
+                           "certification and the exact fallback launch)", bound="tensor", achieved=achieved,
+                    peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops"], traffic=None,
+                    peak_source=peaks["source"] + " (bf16 dense burst)", algorithmic_flops_per_launch=flops,
+                    kernel_ms=t_rank_kernel * 1e3, fallback_rows=st.get("fallback_rows"),
+                    fp32_fma_peak_tflops_measured=fp32_peak)
+    else:
+        roof = dict(kernel="rank_topk_kernel<true>", bound="fp32_fma", achieved=achieved, peak=fp32_peak, unit="TFLOP/s",
+                    frac=achieved / fp32_peak if fp32_peak else None, traffic=None,
+                    peak_source="chaorec_probe_fp32_fma measured live on this GPU (MEASURED_PEAKS.json has no fp32 entry)",
+                    frac_of_bf16_tensor_peak=achieved / peaks["bf16_tflops"], algorithmic_flops_per_launch=flops,
+                    kernel_ms=t_rank_kernel * 1e3)
     out = dict(
         value=value, ms_per_step=t_total / args.steps * 1e3, clocks=clocks,
         e2e=dict(value=e2e_value, unit="users/s", h2d_bytes_per_step=batch.h2d_bytes(), d2h_bytes_per_step=n_local * 8,
                  includes="H2D of embeddings+mask+positives, rank kernel, hits kernel, D2H hit masks, gather, host fp64 metrics"),
-        roofline=dict(kernel="rank_topk_kernel<true>", bound="fp32_fma", achieved=achieved, peak=fp32_peak, unit="TFLOP/s",
-                      frac=achieved / fp32_peak if fp32_peak else None, traffic=None,
-                      peak_source="chaorec_probe_fp32_fma measured live on this GPU (MEASURED_PEAKS.json has no fp32 entry)",
-                      frac_of_bf16_tensor_peak=achieved / peaks["bf16_tflops"], algorithmic_flops_per_launch=flops,
-                      kernel_ms=t_rank_kernel * 1e3),
-        gpu_launches=2 * args.steps,
+        roofline=roof, engine=st.get("engine"),
+        gpu_launches=(7 if tensor else 2) * args.steps,
         config=dict(workload="full-rank top-20 eval, 1M users x 200k items, d=64 (BASELINE configs[3])", users=U, items=I,
                     d=d, topk=K, mask_items_per_user=EVAL_CFG["mask_per_user"], sharding=f"users/{world}",
                     l2="flushed between steps (192 MiB write)", scale=args.scale),
@@ -414,6 +427,8 @@ def run_knn_leg(args, dev, rank, world, peaks):
         x = torch.randn(N, D, device=dev, generator=g)
         if name == "v_feat":
             x = torch.relu(x)
+        kst = {}
+        cb.knn_topk(x, cfg["k"], row_range=(lo, hi), stats=kst)
         for _ in range(max(1, args.warmup - 1)):
             cb.knn_topk(x, cfg["k"], row_range=(lo, hi))
         torch.cuda.synchronize()
@@ -432,7 +447,8 @@ def run_knn_leg(args, dev, rank, world, peaks):
         t = float(tt[0])
         flops = 2.0 * N * N * D
         out[name] = dict(value=N / t, unit="item rows/s", ms=t * 1e3, D=D, N=N, k=cfg["k"], tflops=flops / t / 1e12,
-                         frac_of_bf16_tensor_peak=flops / t / 1e12 / peaks["bf16_tflops"])
+                         frac_of_bf16_tensor_peak=flops / t / 1e12 / peaks["bf16_tflops"], engine=kst.get("engine"),
+                         fallback_rows=kst.get("fallback_rows"))
     return dict(metric="kNN graph item rows/s", config=dict(workload="cosine kNN graph, clothing-shaped (BASELINE configs[2])"), **out)
 
 

@@ -40,7 +40,7 @@ constexpr int kBBytes = BN * BK * 2;   // 16 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kTcThreads = 320;
 constexpr int kEpiWarps = 8;
-constexpr int TC_CAP = 1024;     // candidate slots per row inside a unit
+constexpr int TC_CAP = 512;      // candidate slots per row inside a unit
 constexpr int kTcTrigger = TC_CAP - BN;
 constexpr int KP_MAX = 128;      // K' (approximate candidates kept per (row, slice)) is 64 or 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((128u >> 4) << 24);
@@ -131,40 +131,58 @@ __device__ __forceinline__ void warp_sort_desc_tc(uint64_t *s, int P, int lane) 
     }
 }
 
-// rare path: a score passed the row threshold
-__device__ __noinline__ int tc_append(const TcArgs *__restrict__ a, uint64_t *row_buf, int cnt, int64_t row, int64_t col,
-                                      float s) {
-    if (col >= a->Nb) return cnt;                                  // zero-filled out-of-range column
-    if (a->exclude_self && col == row + a->self_off) return cnt;
-    if (a->mask_rowptr != nullptr) {                               // train items re-enter later at mask_value
+// A listed column is valid unless it is zero padding beyond Nb, the row itself (exclude_self) or a
+// train item of the row (those re-enter at the end with mask_value).  Checked at merge time only,
+// so that the per-score path stays a compare and a store.
+__device__ __forceinline__ bool tc_valid(const TcArgs *__restrict__ a, int64_t row, uint64_t key) {
+    if (key == 0ull) return false;
+    const int64_t col = key_index(key);
+    if (col >= a->Nb) return false;
+    if (a->exclude_self && col == row + a->self_off) return false;
+    if (a->mask_rowptr != nullptr) {
         int64_t lo = a->mask_rowptr[row], hi = a->mask_rowptr[row + 1];
         const int32_t want = static_cast<int32_t>(col);
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
             const int32_t v = a->mask_col[mid];
-            if (v == want) return cnt;
+            if (v == want) return false;
             if (v < want) lo = mid + 1; else hi = mid;
         }
     }
-    if (cnt < TC_CAP) row_buf[cnt] = make_key(s, static_cast<uint32_t>(col));
-    return cnt + 1;
+    return true;
 }
 
-// The warp sorts the list of lane `src`'s row and keeps the best KP; returns (new count, new tau)
-// to every lane (only lane `src` uses them).
-__device__ __forceinline__ void tc_merge(uint64_t *row_buf_src, int n, uint64_t *scratch, int lane, int KP, int &new_cnt,
-                                         float &new_tau) {
+// The warp sorts the list of one row (n entries in row_buf), drops invalid columns and keeps the
+// best KP valid ones (written back to row_buf, best first, and left in scratch[0..kept)).
+// Returns the new count and, when KP valid entries exist, the new threshold (else old_tau).
+__device__ __forceinline__ void tc_merge(const TcArgs *__restrict__ a, int64_t row, uint64_t *row_buf, int n,
+                                         uint64_t *scratch, int lane, int KP, float old_tau, int &new_cnt, float &new_tau) {
     if (n > TC_CAP) n = TC_CAP;
     int P = 64;
     while (P < n) P <<= 1;
-    for (int t = lane; t < P; t += 32) scratch[t] = (t < n) ? row_buf_src[t] : 0ull;
+    for (int t = lane; t < P; t += 32) scratch[t] = (t < n) ? row_buf[t] : 0ull;
     __syncwarp();
     warp_sort_desc_tc(scratch, P, lane);
-    const int keep = n < KP ? n : KP;
-    for (int t = lane; t < keep; t += 32) row_buf_src[t] = scratch[t];
-    new_cnt = keep;
-    new_tau = (n >= KP) ? key_score(scratch[KP - 1]) : -INFINITY;
-    __syncwarp();
+    int kept = 0;
+    uint64_t kth = 0ull;
+    for (int base = 0; base < n && kept < KP; base += 32) {
+        const int i = base + lane;
+        const uint64_t key = (i < n) ? scratch[i] : 0ull;
+        const bool ok = tc_valid(a, row, key);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        const int pos = kept + __popc(m & ((1u << lane) - 1u));
+        __syncwarp();
+        if (ok && pos < KP) {
+            row_buf[pos] = key;
+            scratch[pos] = key;          // pos <= i: compaction never overtakes unread entries of later rounds
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, ok && pos == KP - 1);
+        if (hit) kth = __shfl_sync(0xffffffffu, key, __ffs(hit) - 1);
+        kept += __popc(m);
+        __syncwarp();
+    }
+    new_cnt = kept < KP ? kept : KP;
+    new_tau = (kept >= KP) ? key_score(kth) : old_tau;
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -296,11 +314,14 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
                     for (int j = 0; j < 32; ++j) any |= (__uint_as_float(v[j]) > tau);
                     if (any) {
-                        const int64_t col0 = static_cast<int64_t>(t) * BN + c * 32;
+                        const uint32_t col0 = static_cast<uint32_t>(t) * BN + c * 32;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float s = __uint_as_float(v[j]);
-                            if (s > tau) cnt = tc_append(s_args, row_buf, cnt, row, col0 + j, s);
+                            if (s > tau) {
+                                if (cnt < TC_CAP) row_buf[cnt] = make_key(s, col0 + j);
+                                ++cnt;
+                            }
                         }
                     }
                 }
@@ -314,10 +335,11 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     const int src = __ffs(need) - 1;
                     need &= need - 1;
                     const int n_src = __shfl_sync(0xffffffffu, cnt, src);
+                    const float tau_src = __shfl_sync(0xffffffffu, tau, src);
                     uint64_t *buf_src = a.cand_ws + (static_cast<size_t>(blockIdx.x) * BM + (row_local - lane + src)) * TC_CAP;
                     int nc;
                     float nt;
-                    tc_merge(buf_src, n_src, scratch, lane, KP, nc, nt);
+                    tc_merge(s_args, row - lane + src, buf_src, n_src, scratch, lane, KP, tau_src, nc, nt);
                     if (lane == src) { cnt = nc; tau = nt; }
                 }
             }
@@ -331,16 +353,13 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 uint64_t *buf_src = a.cand_ws + (static_cast<size_t>(blockIdx.x) * BM + (row_local - lane + src)) * TC_CAP;
                 int nc;
                 float nt;
-                tc_merge(buf_src, n_src, scratch, lane, KP, nc, nt);
-                // after tc_merge scratch[0..P) is sorted; entries beyond nc are ignored
+                tc_merge(s_args, row_src, buf_src, n_src, scratch, lane, KP, tau_src, nc, nt);
                 uint64_t *out = a.cand_out + (static_cast<size_t>(row_src) * a.n_slices + sl) * KP;
                 for (int t2 = lane; t2 < KP; t2 += 32) out[t2] = (t2 < nc) ? scratch[t2] : 0ull;
-                if (lane == 0) {
-                    // columns never appended scored <= the threshold in force when they were seen, and
-                    // every threshold is <= the final KP-th best; a list that never filled is complete
-                    const float tp = (n_src >= KP) ? nt : tau_src;
-                    a.tprime_out[static_cast<size_t>(row_src) * a.n_slices + sl] = tp;
-                }
+                // t': every valid column that is not listed scored <= the threshold in force when it
+                // was seen, or was cut by a merge that kept KP valid entries above it; both are <= nt
+                // (= the KP-th valid score if the list is full, else the last threshold, -inf if none).
+                if (lane == 0) a.tprime_out[static_cast<size_t>(row_src) * a.n_slices + sl] = nt;
                 __syncwarp();
             }
         }
@@ -431,6 +450,21 @@ __global__ void __launch_bounds__(kRescoreWarps * 32) rescore_kernel(const Resco
     for (int s = lane; s < a.n_slices; s += 32) tmax = fmaxf(tmax, a.tprime[row * a.n_slices + s]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    // cross-slice cut: only the kp best approximate candidates overall are re-scored; whatever is
+    // cut scored <= the kp-th overall, which also dominates every slice's own cut-off
+    int n_cand = n_in;
+    if (a.n_slices > 1) {
+        int Pa = 64;
+        while (Pa < n_in) Pa <<= 1;
+        for (int t = lane; t < Pa; t += 32) keys[t] = (t < n_in) ? a.cand[static_cast<size_t>(row) * n_in + t] : 0ull;
+        __syncwarp();
+        warp_sort_desc_tc(keys, Pa, lane);
+        if (keys[a.kp] != 0ull) {                       // more than kp valid entries: a cut happens
+            tmax = fmaxf(tmax, key_score(keys[a.kp - 1]));
+        }
+        n_cand = a.kp;
+        __syncwarp();
+    }
     int nm = 0;
     int64_t m_lo = 0;
     if (a.mask_rowptr != nullptr) {
@@ -439,27 +473,43 @@ __global__ void __launch_bounds__(kRescoreWarps * 32) rescore_kernel(const Resco
         nm = len < a.K ? static_cast<int>(len) : a.K;
     }
     int P = 64;
-    while (P < n_in + nm) P <<= 1;
-    for (int t = lane; t < P; t += 32) {
+    while (P < n_cand + nm) P <<= 1;
+    // (read every approximate key before any lane overwrites keys[] with exact ones; n_cand <= 128)
+    uint64_t mine[KP_MAX / 32];
+#pragma unroll
+    for (int r = 0; r < KP_MAX / 32; ++r) {
+        const int t = lane + r * 32;
+        uint64_t ak = 0ull;
+        if (t < n_cand) ak = (a.n_slices > 1) ? keys[t] : a.cand[static_cast<size_t>(row) * n_in + t];
+        mine[r] = ak;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int r = 0; r < KP_MAX / 32; ++r) {
+        const int t = lane + r * 32;
+        if (t >= n_cand) continue;
         uint64_t key = 0ull;
-        if (t < n_in) {
-            const uint64_t ak = a.cand[static_cast<size_t>(row) * n_in + t];
-            if (ak != 0ull) {
-                const uint32_t col = key_index(ak);
-                const float *br = a.B + static_cast<int64_t>(col) * a.D;
-                float acc = 0.0f;
-                for (int k = 0; k < a.D; k += 4) {            // canonical chain: k ascending, one fmaf per term
-                    const float4 x = *reinterpret_cast<const float4 *>(ar + k);
-                    const float4 y = __ldg(reinterpret_cast<const float4 *>(br + k));
-                    acc = fmaf(x.x, y.x, acc);
-                    acc = fmaf(x.y, y.y, acc);
-                    acc = fmaf(x.z, y.z, acc);
-                    acc = fmaf(x.w, y.w, acc);
-                }
-                key = make_key(acc, col);
+        const uint64_t ak = mine[r];
+        if (ak != 0ull) {
+            const uint32_t col = key_index(ak);
+            const float *br = a.B + static_cast<int64_t>(col) * a.D;
+            float acc = 0.0f;
+            for (int k = 0; k < a.D; k += 4) {                // canonical chain: k ascending, one fmaf per term
+                const float4 x = *reinterpret_cast<const float4 *>(ar + k);
+                const float4 y = __ldg(reinterpret_cast<const float4 *>(br + k));
+                acc = fmaf(x.x, y.x, acc);
+                acc = fmaf(x.y, y.y, acc);
+                acc = fmaf(x.z, y.z, acc);
+                acc = fmaf(x.w, y.w, acc);
             }
-        } else if (t < n_in + nm) {
-            const int32_t m = a.mask_col[m_lo + (t - n_in)];
+            key = make_key(acc, col);
+        }
+        keys[t] = key;
+    }
+    for (int t = n_cand + lane; t < P; t += 32) {
+        uint64_t key = 0ull;
+        if (t < n_cand + nm) {
+            const int32_t m = a.mask_col[m_lo + (t - n_cand)];
             if (m >= 0 && m < a.Nb) key = make_key(a.mask_value, static_cast<uint32_t>(m));
         }
         keys[t] = key;
