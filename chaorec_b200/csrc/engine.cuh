@@ -25,6 +25,7 @@ struct EngineArgs {
 
 // exact fp32 CUDA-core engine (rank_topk.cu)
 size_t rank_workspace_bytes(int64_t Ma, int d);
+size_t rank_listed_workspace_bytes(int d);   // row-list mode (two sibling launches + slice buffer)
 int rank_launch_engine(const EngineArgs &e, void *workspace, size_t workspace_bytes, cudaStream_t stm);
 
 // bf16 tcgen05 pre-filter + exact re-score + certification (tc_candidates.cu)

@@ -39,6 +39,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int CAP = 256;           // candidate slots per row
 constexpr int kTrigger = CAP - TI; // a tile can add at most TI entries to a row
 constexpr int kMaxK = 64;
+constexpr int kSliceCapRows = 4096;   // longest row list the column-sliced path accepts
 constexpr int kTileFloats = TU * LDSF;                 // one 128 x 68 tile
 constexpr int kTileBytes = kTileFloats * 4;            // 34816
 constexpr int kScratchKeys = kTileBytes / kWarps / 8;  // 544 keys of sort scratch per warp
@@ -62,6 +63,14 @@ struct RankArgs {
     int n_row_tiles;
     const int32_t *row_list;            // nullable: tile rows are row_list[u0 + r] instead of u0 + r
     const unsigned int *row_count_dev;  // number of listed rows (device memory)
+    // column slicing (row-list mode only): a short list of rows offers too few 128-row tiles to fill
+    // the GPU, so every tile is cut into n_col_slices column ranges that run as independent units;
+    // each unit publishes its K best keys to slice_out and slice_merge_kernel combines them.
+    int n_col_slices;                   // 1 = off
+    int tiles_per_slice;
+    uint64_t *slice_out;                // [kSliceCapRows][n_col_slices][K]
+    int run_if_count_le;                // listed launches: run only if count <= this (sliced) ...
+    int run_if_count_gt;                // ... or only if count > this (unsliced sibling); -1 = always
 };
 
 struct RowState {
@@ -176,14 +185,71 @@ __device__ __forceinline__ void finish_row(const RankArgs &a, RowState *st, uint
     __syncwarp();
 }
 
+// Column-sliced unit: the K best keys of the unit's column range (masked items are left to the
+// merge kernel), sorted best first, zero padded.
+__device__ __forceinline__ void publish_slice(const RankArgs &a, RowState *st, uint64_t *cand_cta, int ul, int64_t slot,
+                                              uint64_t *scratch, int lane) {
+    int n = st->cnt[ul];
+    if (n > CAP) n = CAP;
+    const int P = next_pow2_min64(n);
+    const uint64_t *row = cand_cta + static_cast<size_t>(ul) * CAP;
+    for (int t = lane; t < P; t += 32) scratch[t] = (t < n) ? row[t] : 0ull;
+    __syncwarp();
+    warp_sort_desc(scratch, P, lane);
+    for (int t = lane; t < a.K; t += 32) a.slice_out[slot * a.K + t] = scratch[t];   // scratch[t>=n] is 0
+    __syncwarp();
+}
+
+constexpr int kMergeMax = 2048;   // n_col_slices * K (<= 1024) + K masked, padded to a power of two
+
+// One warp per listed row: the keys of all column slices + the first K masked items -> top K.
+__global__ void __launch_bounds__(64) slice_merge_kernel(const RankArgs a) {
+    __shared__ uint64_t keys_all[2][kMergeMax];
+    const int64_t count = *a.row_count_dev;
+    if (count > a.run_if_count_le) return;
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *keys = keys_all[wib];
+    for (int64_t p = static_cast<int64_t>(blockIdx.x) * 2 + wib; p < count; p += static_cast<int64_t>(gridDim.x) * 2) {
+        const int64_t u = a.row_list[p];
+        const int n_in = a.n_col_slices * a.K;
+        int nm = 0;
+        int64_t m_lo = 0;
+        if (a.mask_rowptr != nullptr) {
+            m_lo = a.mask_rowptr[u];
+            const int64_t len = a.mask_rowptr[u + 1] - m_lo;
+            nm = (len < a.K) ? static_cast<int>(len) : a.K;
+        }
+        int P = 64;
+        while (P < n_in + nm) P <<= 1;
+        for (int t = lane; t < P; t += 32) {
+            uint64_t key = 0ull;
+            if (t < n_in) {
+                key = a.slice_out[p * n_in + t];
+            } else if (t < n_in + nm) {
+                const int32_t m = a.mask_col[m_lo + (t - n_in)];
+                if (m >= 0 && m < a.Nb) key = make_key(a.mask_value, static_cast<uint32_t>(m));
+            }
+            keys[t] = key;
+        }
+        __syncwarp();
+        warp_sort_desc(keys, P, lane);
+        for (int t = lane; t < a.K; t += 32) {
+            const uint64_t key = keys[t];
+            a.out_idx[u * a.K + t] = static_cast<int64_t>(key_index(key)) + a.id_offset;
+            if (a.out_score) a.out_score[u * a.K + t] = key_score(key);
+        }
+        __syncwarp();
+    }
+}
+
 // One ring stage = KC-wide slice c of B tile `it` (+ of the A tile when A is not resident).  Rows
 // are copied one by one so that they land on the padded stride.  The copies are spread over the
 // whole CTA (thread r copies B row r, thread 128+r copies A row r): a single producer warp issuing
 // all 128-256 descriptor-less bulk copies lagged its seven sibling warps by the issue time and the
 // CTA barrier then stalled on it (35 % of warp time in the first ncu capture, profiles/r01_*).
 template <bool A_RESIDENT>
-__device__ __forceinline__ uint32_t stage_tx_bytes(const RankArgs &a, int nu, int64_t q, int nch) {
-    const int it = static_cast<int>(q / nch), c = static_cast<int>(q % nch);
+__device__ __forceinline__ uint32_t stage_tx_bytes(const RankArgs &a, int nu, int64_t q, int nch, int it_lo) {
+    const int it = it_lo + static_cast<int>(q / nch), c = static_cast<int>(q % nch);
     const int kc = (a.d - c * KC < KC) ? (a.d - c * KC) : KC;
     const int64_t i0 = static_cast<int64_t>(it) * TI;
     const int nb = (a.Nb - i0 < TI) ? static_cast<int>(a.Nb - i0) : TI;
@@ -192,8 +258,8 @@ __device__ __forceinline__ uint32_t stage_tx_bytes(const RankArgs &a, int nu, in
 
 template <bool A_RESIDENT>
 __device__ __forceinline__ void issue_stage(const RankArgs &a, float *stage, uint64_t *bar, int64_t u0, int nu,
-                                            int64_t q, int nch, int tid) {
-    const int it = static_cast<int>(q / nch), c = static_cast<int>(q % nch);
+                                            int64_t q, int nch, int it_lo, int tid) {
+    const int it = it_lo + static_cast<int>(q / nch), c = static_cast<int>(q % nch);
     const int kc = (a.d - c * KC < KC) ? (a.d - c * KC) : KC;
     const uint32_t row_bytes = static_cast<uint32_t>(kc) * 4u;
     const int64_t i0 = static_cast<int64_t>(it) * TI;
@@ -253,9 +319,13 @@ __global__ void __launch_bounds__(kThreads, A_RESIDENT ? 2 : 1) rank_topk_kernel
     uint32_t ph0 = 0, ph1 = 0, phA = 0;
     const int nch = (a.d + KC - 1) / KC;
     const int n_it = static_cast<int>((a.Nb + TI - 1) / TI);
-    const int64_t Q = static_cast<int64_t>(n_it) * nch;
     const int64_t Ma_eff = a.row_list ? static_cast<int64_t>(*a.row_count_dev) : a.Ma;
-    const int n_row_tiles = a.row_list ? static_cast<int>((Ma_eff + TU - 1) / TU) : a.n_row_tiles;
+    if (a.row_list) {   // the sliced and the unsliced launch of a row list are siblings: exactly one runs
+        if (a.run_if_count_le >= 0 && Ma_eff > a.run_if_count_le) return;
+        if (a.run_if_count_gt >= 0 && Ma_eff <= a.run_if_count_gt) return;
+    }
+    const int S = a.n_col_slices;
+    const int n_row_tiles = (a.row_list ? static_cast<int>((Ma_eff + TU - 1) / TU) : a.n_row_tiles) * S;
 
     for (;;) {
         if (tid == 0) *s_tile = static_cast<int>(atomicAdd(a.tile_counter, 1u));
@@ -267,22 +337,26 @@ __global__ void __launch_bounds__(kThreads, A_RESIDENT ? 2 : 1) rank_topk_kernel
         __syncthreads();
         const int ut = *s_tile;
         if (ut >= n_row_tiles) break;
-        const int64_t u0 = static_cast<int64_t>(ut) * TU;
+        const int sl = ut % S;
+        const int it_lo = (S > 1) ? sl * a.tiles_per_slice : 0;
+        const int it_hi = (S > 1) ? ((it_lo + a.tiles_per_slice < n_it) ? it_lo + a.tiles_per_slice : n_it) : n_it;
+        const int64_t Q = static_cast<int64_t>(it_hi > it_lo ? it_hi - it_lo : 0) * nch;
+        const int64_t u0 = static_cast<int64_t>(ut / S) * TU;
         const int nu = (Ma_eff - u0 < TU) ? static_cast<int>(Ma_eff - u0) : TU;
 
         // expected byte counts first (one thread), then every thread issues its row copies
         if (tid == 0) {
             if (A_RESIDENT) mbar_arrive_expect_tx(&bars[2], static_cast<uint32_t>(nu) * static_cast<uint32_t>(a.d) * 4u);
-            mbar_arrive_expect_tx(&bars[0], stage_tx_bytes<A_RESIDENT>(a, nu, 0, nch));
-            if (Q > 1) mbar_arrive_expect_tx(&bars[1], stage_tx_bytes<A_RESIDENT>(a, nu, 1, nch));
+            if (Q > 0) mbar_arrive_expect_tx(&bars[0], stage_tx_bytes<A_RESIDENT>(a, nu, 0, nch, it_lo));
+            if (Q > 1) mbar_arrive_expect_tx(&bars[1], stage_tx_bytes<A_RESIDENT>(a, nu, 1, nch, it_lo));
         }
         __syncthreads();
         if (A_RESIDENT && tid < nu) {
             const int64_t ar = a.row_list ? static_cast<int64_t>(a.row_list[u0 + tid]) : u0 + tid;
             bulk_g2s(sA_res + tid * LDSF, a.A + ar * a.d, static_cast<uint32_t>(a.d) * 4u, &bars[2]);
         }
-        issue_stage<A_RESIDENT>(a, stage0, &bars[0], u0, nu, 0, nch, tid);
-        if (Q > 1) issue_stage<A_RESIDENT>(a, stage1, &bars[1], u0, nu, 1, nch, tid);
+        if (Q > 0) issue_stage<A_RESIDENT>(a, stage0, &bars[0], u0, nu, 0, nch, it_lo, tid);
+        if (Q > 1) issue_stage<A_RESIDENT>(a, stage1, &bars[1], u0, nu, 1, nch, it_lo, tid);
         if (A_RESIDENT) {
             mbar_wait(&bars[2], phA);
             phA ^= 1u;
@@ -291,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, A_RESIDENT ? 2 : 1) rank_topk_kernel
         float acc[8][8];
         for (int64_t q = 0; q < Q; ++q) {
             const int s = static_cast<int>(q & 1);
-            const int it = static_cast<int>(q / nch);
+            const int it = it_lo + static_cast<int>(q / nch);
             const int c = static_cast<int>(q % nch);
             float *stage = s ? stage1 : stage0;
             if (s) { mbar_wait(&bars[1], ph1); ph1 ^= 1u; } else { mbar_wait(&bars[0], ph0); ph0 ^= 1u; }
@@ -354,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, A_RESIDENT ? 2 : 1) rank_topk_kernel
             // the barrier of stage s finished its phase when this tile was waited for: arm it for the
             // load that is issued right after the CTA barrier below
             if (tid == 0 && q + 2 < Q)
-                mbar_arrive_expect_tx(s ? &bars[1] : &bars[0], stage_tx_bytes<A_RESIDENT>(a, nu, q + 2, nch));
+                mbar_arrive_expect_tx(s ? &bars[1] : &bars[0], stage_tx_bytes<A_RESIDENT>(a, nu, q + 2, nch, it_lo));
             const int need = __syncthreads_or(flag);  // stage s fully consumed; lists complete
             if (need) {
                 uint64_t *scratch = reinterpret_cast<uint64_t *>(stage) + warp * kScratchKeys;
@@ -365,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, A_RESIDENT ? 2 : 1) rank_topk_kernel
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncthreads();
             }
-            if (q + 2 < Q) issue_stage<A_RESIDENT>(a, stage, s ? &bars[1] : &bars[0], u0, nu, q + 2, nch, tid);
+            if (q + 2 < Q) issue_stage<A_RESIDENT>(a, stage, s ? &bars[1] : &bars[0], u0, nu, q + 2, nch, it_lo, tid);
         }
 
         // every issued stage has been consumed: both stages are free -> sort scratch
@@ -375,7 +449,10 @@ __global__ void __launch_bounds__(kThreads, A_RESIDENT ? 2 : 1) rank_topk_kernel
                 const int ul = warp * (TU / kWarps) + r;
                 if (ul < nu) {
                     const int64_t ar = a.row_list ? static_cast<int64_t>(a.row_list[u0 + ul]) : u0 + ul;
-                    finish_row(a, st, cand_cta, ul, ar, scratch, lane);
+                    if (S > 1)
+                        publish_slice(a, st, cand_cta, ul, (u0 + ul) * S + sl, scratch, lane);
+                    else
+                        finish_row(a, st, cand_cta, ul, ar, scratch, lane);
                 }
             }
         }
@@ -403,16 +480,13 @@ size_t rank_workspace_bytes(int64_t Ma, int d) {
     return 256 + static_cast<size_t>(slots) * TU * CAP * sizeof(uint64_t);
 }
 
-int rank_launch_engine(const EngineArgs &e, void *workspace, size_t workspace_bytes, cudaStream_t stm) {
-    RankArgs a{};
-    a.A = e.A; a.B = e.B; a.Ma = e.Ma; a.Nb = e.Nb; a.d = e.d; a.K = e.K;
-    a.mask_rowptr = e.mask_rowptr; a.mask_col = e.mask_col; a.mask_value = e.mask_value;
-    a.exclude_self = e.exclude_self; a.self_off = e.self_off; a.id_offset = e.id_offset;
-    a.out_idx = e.out_idx; a.out_score = e.out_score;
-    a.row_list = e.row_list; a.row_count_dev = e.row_count_dev;
+size_t rank_listed_workspace_bytes(int d) {
+    // both sibling launches + the per-slice key buffer of the sliced one
+    return 2 * rank_workspace_bytes(0, d) + static_cast<size_t>(kSliceCapRows) * 1024 * sizeof(uint64_t) + 512;
+}
+
+static int launch_rank_kernel(RankArgs a, void *workspace, cudaStream_t stm) {
     const bool resident = a.d <= KC;
-    if (workspace_bytes < rank_workspace_bytes(a.Ma, a.d)) return CHAOREC_E_WORKSPACE;
-    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return CHAOREC_E_ALIGN;
     a.tile_counter = reinterpret_cast<unsigned int *>(workspace);
     a.cand = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(workspace) + 256);
     const int64_t tiles = (a.Ma + TU - 1) / TU;
@@ -432,6 +506,46 @@ int rank_launch_engine(const EngineArgs &e, void *workspace, size_t workspace_by
         rank_topk_kernel<false><<<grid, kThreads, smem, stm>>>(a);
     }
     return launch_status();
+}
+
+int rank_launch_engine(const EngineArgs &e, void *workspace, size_t workspace_bytes, cudaStream_t stm) {
+    RankArgs a{};
+    a.A = e.A; a.B = e.B; a.Ma = e.Ma; a.Nb = e.Nb; a.d = e.d; a.K = e.K;
+    a.mask_rowptr = e.mask_rowptr; a.mask_col = e.mask_col; a.mask_value = e.mask_value;
+    a.exclude_self = e.exclude_self; a.self_off = e.self_off; a.id_offset = e.id_offset;
+    a.out_idx = e.out_idx; a.out_score = e.out_score;
+    a.row_list = e.row_list; a.row_count_dev = e.row_count_dev;
+    a.n_col_slices = 1; a.tiles_per_slice = 0; a.slice_out = nullptr;
+    a.run_if_count_le = -1; a.run_if_count_gt = -1;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return CHAOREC_E_ALIGN;
+    if (a.row_list == nullptr) {
+        if (workspace_bytes < rank_workspace_bytes(a.Ma, a.d)) return CHAOREC_E_WORKSPACE;
+        return launch_rank_kernel(a, workspace, stm);
+    }
+    // Row-list mode (rows the tensor engine could not certify).  Two sibling launches, of which the
+    // device-side count lets exactly one run: a short list is cut into column slices so that it
+    // still fills the GPU, a long list runs as ordinary 128-row tiles.
+    if (workspace_bytes < rank_listed_workspace_bytes(a.d)) return CHAOREC_E_WORKSPACE;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    const size_t one = (rank_workspace_bytes(0, a.d) + 255) & ~static_cast<size_t>(255);
+    const int n_it = static_cast<int>((a.Nb + TI - 1) / TI);
+    int S = 1024 / a.K;
+    if (S > 64) S = 64;
+    if (S > n_it) S = n_it;
+    RankArgs sl = a;
+    sl.n_col_slices = S;
+    sl.tiles_per_slice = (n_it + S - 1) / S;
+    sl.slice_out = reinterpret_cast<uint64_t *>(ws + 2 * one);
+    sl.run_if_count_le = kSliceCapRows;
+    int rc = CHAOREC_OK;
+    if (S > 1) {
+        rc = launch_rank_kernel(sl, ws, stm);
+        if (rc != CHAOREC_OK) return rc;
+        slice_merge_kernel<<<256, 64, 0, stm>>>(sl);
+        a.run_if_count_gt = kSliceCapRows;
+    }
+    rc = launch_rank_kernel(a, ws + one, stm);
+    return rc;
 }
 
 namespace {

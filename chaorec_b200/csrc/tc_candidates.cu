@@ -131,58 +131,94 @@ __device__ __forceinline__ void warp_sort_desc_tc(uint64_t *s, int P, int lane) 
     }
 }
 
-// A listed column is valid unless it is zero padding beyond Nb, the row itself (exclude_self) or a
-// train item of the row (those re-enter at the end with mask_value).  Checked at merge time only,
-// so that the per-score path stays a compare and a store.
-__device__ __forceinline__ bool tc_valid(const TcArgs *__restrict__ a, int64_t row, uint64_t key) {
-    if (key == 0ull) return false;
-    const int64_t col = key_index(key);
-    if (col >= a->Nb) return false;
-    if (a->exclude_self && col == row + a->self_off) return false;
-    if (a->mask_rowptr != nullptr) {
-        int64_t lo = a->mask_rowptr[row], hi = a->mask_rowptr[row + 1];
-        const int32_t want = static_cast<int32_t>(col);
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            const int32_t v = a->mask_col[mid];
-            if (v == want) return false;
-            if (v < want) lo = mid + 1; else hi = mid;
-        }
+constexpr int kKeysPerLane = TC_CAP / 32;
+
+// Mid-run compaction of one row's list (n entries in global memory), executed by a whole warp:
+// a 32-step bitwise search finds the (r+1)-th largest score (keys are spread 16 per lane in
+// registers, counts are combined with redux.sync), entries below it are dropped, the survivors
+// are written back in arbitrary order.  No sort, no validity lookups: r already includes one
+// slot for every column that may later turn out to be invalid (train items, the row itself).
+// Returns the new count and the new threshold (ties at the threshold are kept, so the count can
+// exceed r+1; the caller treats a list that is still too long as uncertifiable).
+__device__ __forceinline__ void tc_select(uint64_t *row_buf, int n, int r, int lane, int &new_cnt, float &new_tau) {
+    uint64_t k[kKeysPerLane];
+#pragma unroll
+    for (int i = 0; i < kKeysPerLane; ++i) {
+        const int idx = lane + 32 * i;
+        k[i] = (idx < n) ? row_buf[idx] : 0ull;
     }
-    return true;
+    uint32_t prefix = 0;
+#pragma unroll 1
+    for (int b = 31; b >= 0; --b) {
+        const uint32_t cand = prefix | (1u << b);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < kKeysPerLane; ++i) c += (static_cast<uint32_t>(k[i] >> 32) >= cand) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= r + 1) prefix = cand;
+    }
+    int mine = 0;
+#pragma unroll
+    for (int i = 0; i < kKeysPerLane; ++i) mine += (k[i] != 0ull && static_cast<uint32_t>(k[i] >> 32) >= prefix) ? 1 : 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int pos = incl - mine;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kKeysPerLane; ++i) {
+        if (k[i] != 0ull && static_cast<uint32_t>(k[i] >> 32) >= prefix) row_buf[pos++] = k[i];
+    }
+    __syncwarp();
+    new_cnt = total;
+    new_tau = score_of_bits(prefix);
 }
 
-// The warp sorts the list of one row (n entries in row_buf), drops invalid columns and keeps the
-// best KP valid ones (written back to row_buf, best first, and left in scratch[0..kept)).
-// Returns the new count and, when KP valid entries exist, the new threshold (else old_tau).
-__device__ __forceinline__ void tc_merge(const TcArgs *__restrict__ a, int64_t row, uint64_t *row_buf, int n,
-                                         uint64_t *scratch, int lane, int KP, float old_tau, int &new_cnt, float &new_tau) {
-    if (n > TC_CAP) n = TC_CAP;
+// End of a unit: sort the (already compacted) list, drop invalid columns -- zero padding beyond Nb
+// is never appended; the row itself (exclude_self) and the row's train items (they re-enter in the
+// re-score kernel with mask_value) are matched against the row's mask list held one entry per lane
+// -- and leave the best KP valid keys in scratch[0..kept).  Returns kept and the cut-off score.
+__device__ __forceinline__ void tc_finish(const TcArgs *__restrict__ a, int64_t row, const uint64_t *row_buf, int n,
+                                          uint64_t *scratch, int lane, int KP, float old_tau, int &kept_out, float &tprime) {
     int P = 64;
     while (P < n) P <<= 1;
     for (int t = lane; t < P; t += 32) scratch[t] = (t < n) ? row_buf[t] : 0ull;
     __syncwarp();
     warp_sort_desc_tc(scratch, P, lane);
+    int64_t m_lo = 0;
+    int nm = 0;
+    if (a->mask_rowptr != nullptr) {
+        m_lo = a->mask_rowptr[row];
+        nm = static_cast<int>(a->mask_rowptr[row + 1] - m_lo);
+    }
+    const int64_t self_col = a->exclude_self ? row + a->self_off : -1;
     int kept = 0;
     uint64_t kth = 0ull;
     for (int base = 0; base < n && kept < KP; base += 32) {
         const int i = base + lane;
         const uint64_t key = (i < n) ? scratch[i] : 0ull;
-        const bool ok = tc_valid(a, row, key);
+        const int64_t col = key_index(key);
+        bool ok = key != 0ull && col != self_col;
+        for (int mb = 0; mb < nm; mb += 32) {             // nm is small (a user's train items)
+            const int32_t mc = (mb + lane < nm) ? a->mask_col[m_lo + mb + lane] : -1;
+            const int lim = (nm - mb < 32) ? (nm - mb) : 32;
+            for (int j = 0; j < lim; ++j) ok = ok && (static_cast<int64_t>(__shfl_sync(0xffffffffu, mc, j)) != col);
+        }
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         const int pos = kept + __popc(m & ((1u << lane) - 1u));
         __syncwarp();
-        if (ok && pos < KP) {
-            row_buf[pos] = key;
-            scratch[pos] = key;          // pos <= i: compaction never overtakes unread entries of later rounds
-        }
+        if (ok && pos < KP) scratch[pos] = key;          // pos <= i: never overtakes unread entries
         const unsigned hit = __ballot_sync(0xffffffffu, ok && pos == KP - 1);
         if (hit) kth = __shfl_sync(0xffffffffu, key, __ffs(hit) - 1);
         kept += __popc(m);
         __syncwarp();
     }
-    new_cnt = kept < KP ? kept : KP;
-    new_tau = (kept >= KP) ? key_score(kth) : old_tau;
+    kept_out = kept < KP ? kept : KP;
+    tprime = (kept >= KP) ? key_score(kth) : old_tau;
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -292,13 +328,23 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         int as = 0;
         uint32_t aphase = 0;
         const int KP = a.kp;
+        const uint32_t nb32 = static_cast<uint32_t>(a.Nb);
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int rt = unit / a.n_slices, sl = unit % a.n_slices;
             const int t_lo = sl * a.tiles_per_slice;
             const int t_hi = min(t_lo + a.tiles_per_slice, n_col_tiles);
             const int64_t row = static_cast<int64_t>(rt) * BM + row_local;
             const bool row_ok = row < a.Ma;
-            float tau = row_ok ? -INFINITY : INFINITY;
+            // r_keep = K' plus one slot for every column that may later prove invalid
+            int r_keep = KP + (a.exclude_self ? 1 : 0);
+            if (row_ok && a.mask_rowptr != nullptr) {
+                const int64_t len = a.mask_rowptr[row + 1] - a.mask_rowptr[row];
+                r_keep += (len < TC_CAP) ? static_cast<int>(len) : TC_CAP;
+            }
+            // a row whose kept set could not leave room for a tile of appends (a user with hundreds of
+            // train items) is not pre-filtered at all: it goes to the exact engine
+            bool give_up = row_ok && (r_keep + 64 > kTcTrigger);
+            float tau = (row_ok && !give_up) ? -INFINITY : INFINITY;
             int cnt = 0;
             for (int t = t_lo; t < t_hi; ++t) {
                 mbar_wait(&tfull_bar[as], aphase);
@@ -318,7 +364,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float s = __uint_as_float(v[j]);
-                            if (s > tau) {
+                            if (s > tau && col0 + j < nb32) {     // (zero padding beyond Nb is never listed)
                                 if (cnt < TC_CAP) row_buf[cnt] = make_key(s, col0 + j);
                                 ++cnt;
                             }
@@ -328,38 +374,62 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[as]);                     // this thread is done with the stage
                 if (++as == 2) { as = 0; aphase ^= 1u; }
-                // lists that could overflow during the next tile are compacted now (warp-cooperative)
+                // Compaction.  A warp that compacts holds up the accumulator ring for everybody, so
+                // compactions are batched: all rows of the CTA compact together after tiles 2, 8, 32,
+                // 128, ... of the unit (the threshold then rises fast enough that a list never fills in
+                // between on ordinary data); a list that does get close to full compacts at once.
+                const int lt = t - t_lo;
+                const bool burst = lt >= 2 && (lt & (lt - 1)) == 0 && ((__ffs(lt) - 1) & 1);
                 __syncwarp();                                     // appended keys visible to the whole warp
-                unsigned need = __ballot_sync(0xffffffffu, cnt > kTcTrigger);
+                unsigned need = __ballot_sync(0xffffffffu, cnt > kTcTrigger || (burst && cnt > r_keep + 32));
                 while (need) {
                     const int src = __ffs(need) - 1;
                     need &= need - 1;
                     const int n_src = __shfl_sync(0xffffffffu, cnt, src);
-                    const float tau_src = __shfl_sync(0xffffffffu, tau, src);
+                    const int r_src = __shfl_sync(0xffffffffu, r_keep, src);
                     uint64_t *buf_src = a.cand_ws + (static_cast<size_t>(blockIdx.x) * BM + (row_local - lane + src)) * TC_CAP;
                     int nc;
                     float nt;
-                    tc_merge(s_args, row - lane + src, buf_src, n_src, scratch, lane, KP, tau_src, nc, nt);
-                    if (lane == src) { cnt = nc; tau = nt; }
+                    tc_select(buf_src, n_src < TC_CAP ? n_src : TC_CAP, r_src, lane, nc, nt);
+                    if (lane == src) {
+                        if (n_src > TC_CAP || nc > kTcTrigger) {  // overflowed, or a huge run of exact ties
+                            give_up = true;
+                            tau = INFINITY;
+                            cnt = 0;
+                        } else {
+                            cnt = nc;
+                            tau = nt;
+                        }
+                    }
                 }
             }
-            // ---- end of unit: sort every row's list, publish the best KP and the cut-off t' ----
+            // ---- end of unit: publish the best KP valid candidates of every row and the cut-off t' ----
             __syncwarp();
             for (int src = 0; src < 32; ++src) {
-                const int n_src = __shfl_sync(0xffffffffu, cnt, src);
-                const float tau_src = __shfl_sync(0xffffffffu, tau, src);
+                int n_src = __shfl_sync(0xffffffffu, cnt, src);
+                float tau_src = __shfl_sync(0xffffffffu, tau, src);
+                const int r_src = __shfl_sync(0xffffffffu, r_keep, src);
+                const int gu_src = __shfl_sync(0xffffffffu, give_up ? 1 : 0, src);
                 const int64_t row_src = row - lane + src;
                 if (row_src >= a.Ma) continue;                    // warp-uniform
-                uint64_t *buf_src = a.cand_ws + (static_cast<size_t>(blockIdx.x) * BM + (row_local - lane + src)) * TC_CAP;
-                int nc;
-                float nt;
-                tc_merge(s_args, row_src, buf_src, n_src, scratch, lane, KP, tau_src, nc, nt);
                 uint64_t *out = a.cand_out + (static_cast<size_t>(row_src) * a.n_slices + sl) * KP;
+                float tp = INFINITY;                              // +inf: cannot be certified -> exact engine
+                int nc = 0;
+                if (!gu_src && n_src <= TC_CAP) {
+                    uint64_t *buf_src = a.cand_ws + (static_cast<size_t>(blockIdx.x) * BM + (row_local - lane + src)) * TC_CAP;
+                    if (n_src > r_src + 1) {                      // cut to the r_keep best before sorting
+                        float nt;
+                        tc_select(buf_src, n_src, r_src, lane, n_src, nt);
+                        tau_src = nt;
+                    }
+                    if (n_src <= kTcTrigger) {
+                        // every valid column that is not listed scored <= the threshold in force when it
+                        // was seen, or was cut by a compaction that kept KP valid entries above it
+                        tc_finish(s_args, row_src, buf_src, n_src, scratch, lane, KP, tau_src, nc, tp);
+                    }
+                }
                 for (int t2 = lane; t2 < KP; t2 += 32) out[t2] = (t2 < nc) ? scratch[t2] : 0ull;
-                // t': every valid column that is not listed scored <= the threshold in force when it
-                // was seen, or was cut by a merge that kept KP valid entries above it; both are <= nt
-                // (= the KP-th valid score if the list is full, else the last threshold, -inf if none).
-                if (lane == 0) a.tprime_out[static_cast<size_t>(row_src) * a.n_slices + sl] = nt;
+                if (lane == 0) a.tprime_out[static_cast<size_t>(row_src) * a.n_slices + sl] = tp;
                 __syncwarp();
             }
         }
@@ -592,7 +662,7 @@ size_t tc_workspace_bytes(int64_t Ma, int64_t Nb, int D) {
     n += al256(static_cast<size_t>(Ma) * slices * KP_MAX * 8);          // published candidates
     n += al256(static_cast<size_t>(Ma) * slices * 4);                   // t'
     n += al256(static_cast<size_t>(Ma) * 4);                            // fallback row list
-    n += rank_workspace_bytes(Ma, D);                                   // exact engine for uncertified rows
+    n += rank_listed_workspace_bytes(D);                                // exact engine for uncertified rows
     return n;
 }
 

@@ -220,3 +220,21 @@ def test_tensor_engine_is_used_and_rarely_falls_back(canon, engine):
     idx = cb.rank_topk(u.to(dev()), it2.to(dev()), None, K, 1e-6, 0, stats=stats)
     cidx, _ = canon.score_mask_topk(u.numpy(), it2.numpy(), None, None, 1e-6, K, 0)
     assert np.array_equal(idx.cpu().numpy(), cidx)
+    if engine == "auto":
+        assert 0 < stats["fallback_rows"] <= 4096          # short list -> column-sliced exact pass
+    # every item within bf16 resolution of every other: nothing can be certified, all 5000 rows take
+    # the unsliced exact pass
+    it3 = it[5].unsqueeze(0) * (1.0 + 1e-5 * torch.arange(I).float().unsqueeze(1))
+    stats = {}
+    idx = cb.rank_topk(u.to(dev()), it3.to(dev()), mask, K, 1e-6, 0, stats=stats)
+    cidx, _ = canon.score_mask_topk(u.numpy(), it3.numpy(), rp, col, 1e-6, K, 0)
+    assert np.array_equal(idx.cpu().numpy(), cidx)
+    if engine == "auto":
+        assert stats["fallback_rows"] > 4096
+    # a user with hundreds of train items is handed to the exact engine up front
+    heavy = cb.mask_csr_from_edges(torch.cat((tu, torch.zeros(400, dtype=torch.int64))).to(dev()),
+                                   torch.cat((ti, torch.arange(400))).to(dev()), U, I)
+    idx = cb.rank_topk(u.to(dev()), it.to(dev()), heavy, K, 1e-6, 0)
+    hrp, hcol = _csr_np(heavy)
+    cidx, _ = canon.score_mask_topk(u.numpy(), it.numpy(), hrp, hcol, 1e-6, K, 0)
+    assert np.array_equal(idx.cpu().numpy(), cidx)
