@@ -206,7 +206,10 @@ __device__ __forceinline__ void tc_finish(const TcArgs *__restrict__ a, int64_t 
         for (int mb = 0; mb < nm; mb += 32) {             // nm is small (a user's train items)
             const int32_t mc = (mb + lane < nm) ? a->mask_col[m_lo + mb + lane] : -1;
             const int lim = (nm - mb < 32) ? (nm - mb) : 32;
-            for (int j = 0; j < lim; ++j) ok = ok && (static_cast<int64_t>(__shfl_sync(0xffffffffu, mc, j)) != col);
+            for (int j = 0; j < lim; ++j) {
+                const int64_t mj = __shfl_sync(0xffffffffu, mc, j);   // every lane takes part (no short-circuit)
+                ok = ok && (mj != col);
+            }
         }
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         const int pos = kept + __popc(m & ((1u << lane) - 1u));
