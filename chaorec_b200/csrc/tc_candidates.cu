@@ -34,10 +34,19 @@ namespace {
 constexpr int BM = 256;          // rows of A per unit (two MMA halves of 128)
 constexpr int BN = 128;          // columns per accumulator tile
 constexpr int BK = 64;           // bf16 elements per pipeline stage (= one 128-byte swizzle row)
-constexpr int kStages = 3;
 constexpr int kABytes = BM * BK * 2;   // 32 KB
 constexpr int kBBytes = BN * BK * 2;   // 16 KB
-constexpr int kStageBytes = kABytes + kBBytes;
+// Two pipeline shapes.  D > 64: every stage carries a K-slab of A and of B (3 x 48 KB).  D <= 64
+// (the evaluation path, one K-slab in total): the A slab is loaded once per unit and stays
+// resident, the ring carries B slabs only (6 x 16 KB) -> a third of the L2->SM traffic per tile
+// and twice as many loads in flight.
+template <bool A_RES> struct Pipe {
+    static constexpr int kStages = A_RES ? 6 : 3;
+    static constexpr int kStageBytes = A_RES ? kBBytes : (kABytes + kBBytes);
+    static constexpr int kRingOff = A_RES ? kABytes : 0;
+    static constexpr int kRingBytes = kRingOff + kStages * kStageBytes;
+    static constexpr int kNumBars = 2 * kStages + 4 + 2;   // full/empty ring, tmem full/empty x2, A full/empty
+};
 constexpr int kTcThreads = 320;
 constexpr int kEpiWarps = 8;
 constexpr int TC_CAP = 512;      // candidate slots per row inside a unit
@@ -224,18 +233,24 @@ __device__ __forceinline__ void tc_finish(const TcArgs *__restrict__ a, int64_t 
     tprime = (kept >= KP) ? key_score(kth) : old_tau;
 }
 
+template <bool A_RES>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcArgs a) {
+    constexpr int kStages = Pipe<A_RES>::kStages;
+    constexpr int kStageBytes = Pipe<A_RES>::kStageBytes;
     extern __shared__ __align__(1024) unsigned char tc_smem[];
-    // layout: [stage 0..2: A slab | B slab] [sort scratch 8 x 8 KB] [barriers] [tmem base] [args]
-    unsigned char *stages = tc_smem;
-    uint64_t *scratch_all = reinterpret_cast<uint64_t *>(tc_smem + kStages * kStageBytes);
+    // layout: [resident A slab (A_RES)] [ring stages] [sort scratch 8 x 4 KB] [barriers] [tmem base] [args]
+    unsigned char *a_res = tc_smem;
+    unsigned char *stages = tc_smem + Pipe<A_RES>::kRingOff;
+    uint64_t *scratch_all = reinterpret_cast<uint64_t *>(tc_smem + Pipe<A_RES>::kRingBytes);
     uint64_t *bars = scratch_all + kEpiWarps * TC_CAP;
     uint64_t *full_bar = bars;                    // [kStages]
     uint64_t *empty_bar = bars + kStages;         // [kStages]
     uint64_t *tfull_bar = bars + 2 * kStages;     // [2]
     uint64_t *tempty_bar = bars + 2 * kStages + 2;  // [2]
-    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+    uint64_t *afull_bar = bars + 2 * kStages + 4;   // resident A slab landed
+    uint64_t *aempty_bar = bars + 2 * kStages + 5;  // every MMA reading the resident A slab retired
+    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + Pipe<A_RES>::kNumBars);
     TcArgs *s_args = reinterpret_cast<TcArgs *>(tmem_base_smem + 4);
 
     const int warp = threadIdx.x >> 5;
@@ -251,6 +266,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             mbar_init(&tfull_bar[s], 1);
             mbar_init(&tempty_bar[s], kEpiWarps * 32);
         }
+        mbar_init(afull_bar, 1);
+        mbar_init(aempty_bar, 1);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_base_smem, 512);
@@ -267,18 +284,24 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, uphase = 0;
             for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
                 const int rt = unit / a.n_slices, sl = unit % a.n_slices;
                 const int t_lo = sl * a.tiles_per_slice;
                 const int t_hi = min(t_lo + a.tiles_per_slice, n_col_tiles);
+                if (A_RES) {
+                    mbar_wait(aempty_bar, uphase ^ 1u);           // previous unit's MMAs are done with the slab
+                    mbar_arrive_expect_tx(afull_bar, kABytes);
+                    tma_load_2d(a_res, &map_a, 0, rt * BM, afull_bar);
+                    uphase ^= 1u;
+                }
                 for (int t = t_lo; t < t_hi; ++t) {
                     for (int kc = 0; kc < n_kc; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
                         unsigned char *sa = stages + stage * kStageBytes;
                         mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-                        tma_load_2d(sa, &map_a, kc * BK, rt * BM, &full_bar[stage]);
-                        tma_load_2d(sa + kABytes, &map_b, kc * BK, t * BN, &full_bar[stage]);
+                        if (!A_RES) tma_load_2d(sa, &map_a, kc * BK, rt * BM, &full_bar[stage]);
+                        tma_load_2d(sa + (A_RES ? 0 : kABytes), &map_b, kc * BK, t * BN, &full_bar[stage]);
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -288,13 +311,18 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // ================= MMA issuer =================
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, uphase = 0;
             int as = 0;
             uint32_t aphase = 0;
             for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
                 const int sl = unit % a.n_slices;
                 const int t_lo = sl * a.tiles_per_slice;
                 const int t_hi = min(t_lo + a.tiles_per_slice, n_col_tiles);
+                if (A_RES) {
+                    mbar_wait(afull_bar, uphase);
+                    uphase ^= 1u;
+                    tc_fence_after();
+                }
                 for (int t = t_lo; t < t_hi; ++t) {
                     mbar_wait(&tempty_bar[as], aphase ^ 1u);      // epilogue drained this accumulator stage
                     tc_fence_after();
@@ -302,9 +330,10 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         mbar_wait(&full_bar[stage], phase);       // TMA bytes have landed
                         tc_fence_after();
                         const unsigned char *sa = stages + stage * kStageBytes;
-                        const uint64_t da0 = smem_desc(sa);
-                        const uint64_t da1 = smem_desc(sa + 128 * BK * 2);
-                        const uint64_t db = smem_desc(sa + kABytes);
+                        const unsigned char *pa = A_RES ? a_res : sa;
+                        const uint64_t da0 = smem_desc(pa);
+                        const uint64_t da1 = smem_desc(pa + 128 * BK * 2);
+                        const uint64_t db = smem_desc(sa + (A_RES ? 0 : kABytes));
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint32_t acc = (kc > 0 || k > 0) ? 1u : 0u;
@@ -318,6 +347,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     umma_commit(&tfull_bar[as]);                  // accumulators complete
                     if (++as == 2) { as = 0; aphase ^= 1u; }
                 }
+                if (A_RES) umma_commit(aempty_bar);               // resident A slab free once this unit's MMAs retire
             }
         }
     } else {
@@ -359,17 +389,22 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     __syncwarp();
                     tmem_ld32(taddr + c * 32, v);
                     tmem_ld_wait();
-                    bool any = false;
+                    // two-level filter: the maximum of every group of 8 columns first (one FMNMX3 chain),
+                    // only groups in which some row beats its threshold are looked at column by column
+                    const uint32_t col0 = static_cast<uint32_t>(t) * BN + c * 32;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) any |= (__uint_as_float(v[j]) > tau);
-                    if (any) {
-                        const uint32_t col0 = static_cast<uint32_t>(t) * BN + c * 32;
+                    for (int g = 0; g < 4; ++g) {
+                        float m = __uint_as_float(v[8 * g]);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float s = __uint_as_float(v[j]);
-                            if (s > tau && col0 + j < nb32) {     // (zero padding beyond Nb is never listed)
-                                if (cnt < TC_CAP) row_buf[cnt] = make_key(s, col0 + j);
-                                ++cnt;
+                        for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[8 * g + j]));
+                        if (m > tau) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float s = __uint_as_float(v[8 * g + j]);
+                                if (s > tau && col0 + 8 * g + j < nb32) {   // (zero padding beyond Nb is never listed)
+                                    if (cnt < TC_CAP) row_buf[cnt] = make_key(s, col0 + 8 * g + j);
+                                    ++cnt;
+                                }
                             }
                         }
                     }
@@ -443,9 +478,10 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+template <bool A_RES>
 constexpr size_t tc_smem_bytes() {
-    return static_cast<size_t>(kStages) * kStageBytes + static_cast<size_t>(kEpiWarps) * TC_CAP * 8 + (2 * kStages + 4) * 8 + 16 +
-           sizeof(TcArgs) + 64;
+    return static_cast<size_t>(Pipe<A_RES>::kRingBytes) + static_cast<size_t>(kEpiWarps) * TC_CAP * 8 +
+           Pipe<A_RES>::kNumBars * 8 + 16 + sizeof(TcArgs) + 64;
 }
 
 // ---- fp32 -> bf16 operand copies (+ row norms for the error bound) ------------------------------
@@ -714,13 +750,18 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     t.cand_ws = cand_ws; t.cand_out = cand_out; t.tprime_out = tprime; t.kp = kp;
     const int n_units = t.n_row_tiles * slices;
     const int grid = n_units < sm_count() ? n_units : sm_count();
-    const size_t smem = tc_smem_bytes();
-    if (cudaFuncSetAttribute(tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
-        cudaSuccess) {
-        cudaGetLastError();
-        return CHAOREC_E_LAUNCH;
+    cudaError_t ce;
+    if (e.d <= BK) {
+        const size_t smem = tc_smem_bytes<true>();
+        ce = cudaFuncSetAttribute(tc_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (ce != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
+        tc_candidates_kernel<true><<<grid, kTcThreads, smem, stm>>>(map_a, map_b, t);
+    } else {
+        const size_t smem = tc_smem_bytes<false>();
+        ce = cudaFuncSetAttribute(tc_candidates_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (ce != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
+        tc_candidates_kernel<false><<<grid, kTcThreads, smem, stm>>>(map_a, map_b, t);
     }
-    tc_candidates_kernel<<<grid, kTcThreads, smem, stm>>>(map_a, map_b, t);
 
     RescoreArgs r{};
     r.A = e.A; r.B = e.B; r.Ma = e.Ma; r.Nb = e.Nb; r.D = e.d; r.K = e.K; r.n_slices = slices; r.kp = kp;
