@@ -116,6 +116,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// back-off wait for the long, latency-insensitive waits of the single-lane producer / MMA roles
+// (a tight try_wait loop steals issue slots from the epilogue warps on the same scheduler)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 
 __device__ __forceinline__ uint64_t smem_desc(const void *p) {
     return (static_cast<uint64_t>(kDescHi) << 32) | static_cast<uint64_t>((smem_u32(p) >> 4) & 0x3FFFu);
@@ -138,6 +143,37 @@ __device__ __forceinline__ void warp_sort_desc_tc(uint64_t *s, int P, int lane) 
             __syncwarp();
         }
     }
+}
+
+// One 32-column chunk of one row: returns the new list length.
+__device__ __forceinline__ int filter_chunk(const uint32_t (&v)[32], float tau, uint32_t col0, uint32_t nb32, bool last_tile,
+                                            uint64_t *row_buf, int cnt) {
+    float m[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float a0 = fmaxf(fmaxf(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
+        const float a1 = fmaxf(fmaxf(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4])), __uint_as_float(v[8 * g + 5]));
+        const float a2 = fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
+        m[g] = fmaxf(fmaxf(a0, a1), a2);
+    }
+    const float mall = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+    if (mall > tau) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (m[g] > tau) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float s = __uint_as_float(v[8 * g + j]);
+                    // (zero padding beyond Nb exists in the last tile only and is never listed)
+                    if (s > tau && (!last_tile || col0 + 8 * g + j < nb32)) {
+                        if (cnt < TC_CAP) row_buf[cnt] = make_key(s, col0 + 8 * g + j);
+                        ++cnt;
+                    }
+                }
+            }
+        }
+    }
+    return cnt;
 }
 
 constexpr int kKeysPerLane = TC_CAP / 32;
@@ -290,14 +326,14 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int t_lo = sl * a.tiles_per_slice;
                 const int t_hi = min(t_lo + a.tiles_per_slice, n_col_tiles);
                 if (A_RES) {
-                    mbar_wait(aempty_bar, uphase ^ 1u);           // previous unit's MMAs are done with the slab
+                    mbar_wait_backoff(aempty_bar, uphase ^ 1u);   // previous unit's MMAs are done with the slab
                     mbar_arrive_expect_tx(afull_bar, kABytes);
                     tma_load_2d(a_res, &map_a, 0, rt * BM, afull_bar);
                     uphase ^= 1u;
                 }
                 for (int t = t_lo; t < t_hi; ++t) {
                     for (int kc = 0; kc < n_kc; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        mbar_wait_backoff(&empty_bar[stage], phase ^ 1u);
                         unsigned char *sa = stages + stage * kStageBytes;
                         mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
                         if (!A_RES) tma_load_2d(sa, &map_a, kc * BK, rt * BM, &full_bar[stage]);
@@ -324,7 +360,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     tc_fence_after();
                 }
                 for (int t = t_lo; t < t_hi; ++t) {
-                    mbar_wait(&tempty_bar[as], aphase ^ 1u);      // epilogue drained this accumulator stage
+                    mbar_wait_backoff(&tempty_bar[as], aphase ^ 1u);   // epilogue drained this accumulator stage
                     tc_fence_after();
                     for (int kc = 0; kc < n_kc; ++kc) {
                         mbar_wait(&full_bar[stage], phase);       // TMA bytes have landed
@@ -383,31 +419,24 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 mbar_wait(&tfull_bar[as], aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * 2 + h) * BN;
+                // 32-column chunks, software-pipelined: the next chunk's tcgen05.ld is in flight while the
+                // current one is filtered.  Filter = maxima of the four 8-column groups (independent
+                // FMNMX3 trees), one combined test, then only the groups in which this row beats its
+                // threshold are looked at column by column.
+                const bool last_tile = (t == n_col_tiles - 1);
+                uint32_t va[32], vb[32];
+                __syncwarp();
+                tmem_ld32(taddr, va);
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t v[32];
-                    __syncwarp();
-                    tmem_ld32(taddr + c * 32, v);
+                for (int c = 0; c < BN / 32; c += 2) {
                     tmem_ld_wait();
-                    // two-level filter: the maximum of every group of 8 columns first (one FMNMX3 chain),
-                    // only groups in which some row beats its threshold are looked at column by column
-                    const uint32_t col0 = static_cast<uint32_t>(t) * BN + c * 32;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float m = __uint_as_float(v[8 * g]);
-#pragma unroll
-                        for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[8 * g + j]));
-                        if (m > tau) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float s = __uint_as_float(v[8 * g + j]);
-                                if (s > tau && col0 + 8 * g + j < nb32) {   // (zero padding beyond Nb is never listed)
-                                    if (cnt < TC_CAP) row_buf[cnt] = make_key(s, col0 + 8 * g + j);
-                                    ++cnt;
-                                }
-                            }
-                        }
-                    }
+                    __syncwarp();
+                    tmem_ld32(taddr + (c + 1) * 32, vb);
+                    cnt = filter_chunk(va, tau, static_cast<uint32_t>(t) * BN + c * 32, nb32, last_tile, row_buf, cnt);
+                    tmem_ld_wait();
+                    __syncwarp();
+                    if (c + 2 < BN / 32) tmem_ld32(taddr + (c + 2) * 32, va);
+                    cnt = filter_chunk(vb, tau, static_cast<uint32_t>(t) * BN + (c + 1) * 32, nb32, last_tile, row_buf, cnt);
                 }
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[as]);                     // this thread is done with the stage
