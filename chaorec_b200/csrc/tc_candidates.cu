@@ -47,10 +47,11 @@ template <bool A_RES> struct Pipe {
     static constexpr int kRingBytes = kRingOff + kStages * kStageBytes;
     static constexpr int kNumBars = 2 * kStages + 4 + 2;   // full/empty ring, tmem full/empty x2, A full/empty
 };
-constexpr int kTcThreads = 320;
-constexpr int kEpiWarps = 8;
-constexpr int TC_CAP = 512;      // candidate slots per row inside a unit
-constexpr int kTcTrigger = TC_CAP - BN;
+constexpr int kTcThreads = 576;   // 2 role warps + 16 epilogue warps
+constexpr int kEpiWarps = 16;
+constexpr int kColHalves = 2;     // two epilogue threads per row, one per 64-column half of every tile
+constexpr int TC_CAP = 256;      // candidate slots per (row, column half) list inside a unit
+constexpr int kTcTrigger = TC_CAP - BN / kColHalves;   // a tile adds at most 64 entries to a list
 constexpr int KP_MAX = 128;      // K' (approximate candidates kept per (row, slice)) is 64 or 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO=1024 B, version 1, SWIZZLE_128B
@@ -64,9 +65,9 @@ struct TcArgs {
     const int32_t *mask_col;
     int exclude_self;
     int64_t self_off;
-    uint64_t *cand_ws;        // [gridDim.x][BM][TC_CAP]
-    uint64_t *cand_out;       // [Ma][n_slices][KP] approximate keys, best first (0 = empty)
-    float *tprime_out;        // [Ma][n_slices] approx score of the KP-th kept candidate (-inf: list complete)
+    uint64_t *cand_ws;        // [gridDim.x][BM][kColHalves][TC_CAP]
+    uint64_t *cand_out;       // [Ma][n_slices*kColHalves][KP] approximate keys, best first (0 = empty)
+    float *tprime_out;        // [Ma][n_slices*kColHalves] approx score of the KP-th kept candidate (-inf: list complete)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -300,7 +301,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], kEpiWarps * 32);
+            mbar_init(&tempty_bar[s], kEpiWarps);
         }
         mbar_init(afull_bar, 1);
         mbar_init(aempty_bar, 1);
@@ -388,14 +389,17 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
     } else {
         // ================= epilogue: one thread per row =================
-        const int ew = warp - 2;                 // 0..7
+        const int ew = warp - 2;                 // 0..15
         const int q = warp & 3;                  // TMEM lane quadrant this warp may access
-        const int h = ew >> 2;                   // which 128-row half
+        const int h = (ew >> 2) & 1;             // which 128-row half
+        const int ch = ew >> 3;                  // which 64-column half of every tile
         const int row_local = h * 128 + q * 32 + lane;
         uint64_t *scratch = scratch_all + ew * TC_CAP;
-        uint64_t *row_buf = a.cand_ws + (static_cast<size_t>(blockIdx.x) * BM + row_local) * TC_CAP;
+        const size_t list0 = (static_cast<size_t>(blockIdx.x) * BM + (row_local - lane)) * kColHalves + ch;   // lane 0's list
+        uint64_t *row_buf = a.cand_ws + (list0 + static_cast<size_t>(lane) * kColHalves) * TC_CAP;
         int as = 0;
         uint32_t aphase = 0;
+        const int n_lists = a.n_slices * kColHalves;
         const int KP = a.kp;
         const uint32_t nb32 = static_cast<uint32_t>(a.Nb);
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -412,7 +416,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
             // a row whose kept set could not leave room for a tile of appends (a user with hundreds of
             // train items) is not pre-filtered at all: it goes to the exact engine
-            bool give_up = row_ok && (r_keep + 64 > kTcTrigger);
+            bool give_up = row_ok && (r_keep + 32 > kTcTrigger);
             float tau = (row_ok && !give_up) ? -INFINITY : INFINITY;
             int cnt = 0;
             for (int t = t_lo; t < t_hi; ++t) {
@@ -424,22 +428,19 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 // FMNMX3 trees), one combined test, then only the groups in which this row beats its
                 // threshold are looked at column by column.
                 const bool last_tile = (t == n_col_tiles - 1);
+                const uint32_t tcol = static_cast<uint32_t>(t) * BN + ch * 64;
                 uint32_t va[32], vb[32];
                 __syncwarp();
-                tmem_ld32(taddr, va);
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; c += 2) {
-                    tmem_ld_wait();
-                    __syncwarp();
-                    tmem_ld32(taddr + (c + 1) * 32, vb);
-                    cnt = filter_chunk(va, tau, static_cast<uint32_t>(t) * BN + c * 32, nb32, last_tile, row_buf, cnt);
-                    tmem_ld_wait();
-                    __syncwarp();
-                    if (c + 2 < BN / 32) tmem_ld32(taddr + (c + 2) * 32, va);
-                    cnt = filter_chunk(vb, tau, static_cast<uint32_t>(t) * BN + (c + 1) * 32, nb32, last_tile, row_buf, cnt);
-                }
+                tmem_ld32(taddr + ch * 64, va);
+                tmem_ld_wait();
+                __syncwarp();
+                tmem_ld32(taddr + ch * 64 + 32, vb);
+                cnt = filter_chunk(va, tau, tcol, nb32, last_tile, row_buf, cnt);
+                tmem_ld_wait();
+                cnt = filter_chunk(vb, tau, tcol + 32, nb32, last_tile, row_buf, cnt);
                 tc_fence_before();
-                mbar_arrive(&tempty_bar[as]);                     // this thread is done with the stage
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[as]);      // this warp is done with the stage
                 if (++as == 2) { as = 0; aphase ^= 1u; }
                 // Compaction.  A warp that compacts holds up the accumulator ring for everybody, so
                 // compactions are batched: all rows of the CTA compact together after tiles 2, 8, 32,
@@ -454,7 +455,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     need &= need - 1;
                     const int n_src = __shfl_sync(0xffffffffu, cnt, src);
                     const int r_src = __shfl_sync(0xffffffffu, r_keep, src);
-                    uint64_t *buf_src = a.cand_ws + (static_cast<size_t>(blockIdx.x) * BM + (row_local - lane + src)) * TC_CAP;
+                    uint64_t *buf_src = a.cand_ws + (list0 + static_cast<size_t>(src) * kColHalves) * TC_CAP;
                     int nc;
                     float nt;
                     tc_select(buf_src, n_src < TC_CAP ? n_src : TC_CAP, r_src, lane, nc, nt);
@@ -479,11 +480,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int gu_src = __shfl_sync(0xffffffffu, give_up ? 1 : 0, src);
                 const int64_t row_src = row - lane + src;
                 if (row_src >= a.Ma) continue;                    // warp-uniform
-                uint64_t *out = a.cand_out + (static_cast<size_t>(row_src) * a.n_slices + sl) * KP;
+                const int list_id = sl * kColHalves + ch;
+                uint64_t *out = a.cand_out + (static_cast<size_t>(row_src) * n_lists + list_id) * KP;
                 float tp = INFINITY;                              // +inf: cannot be certified -> exact engine
                 int nc = 0;
                 if (!gu_src && n_src <= TC_CAP) {
-                    uint64_t *buf_src = a.cand_ws + (static_cast<size_t>(blockIdx.x) * BM + (row_local - lane + src)) * TC_CAP;
+                    uint64_t *buf_src = a.cand_ws + (list0 + static_cast<size_t>(src) * kColHalves) * TC_CAP;
                     if (n_src > r_src + 1) {                      // cut to the r_keep best before sorting
                         float nt;
                         tc_select(buf_src, n_src, r_src, lane, n_src, nt);
@@ -496,7 +498,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     }
                 }
                 for (int t2 = lane; t2 < KP; t2 += 32) out[t2] = (t2 < nc) ? scratch[t2] : 0ull;
-                if (lane == 0) a.tprime_out[static_cast<size_t>(row_src) * a.n_slices + sl] = tp;
+                if (lane == 0) a.tprime_out[static_cast<size_t>(row_src) * n_lists + list_id] = tp;
                 __syncwarp();
             }
         }
@@ -726,9 +728,9 @@ size_t tc_workspace_bytes(int64_t Ma, int64_t Nb, int D) {
     n += al256(static_cast<size_t>(Ma) * D * 2);                        // A bf16
     n += al256(static_cast<size_t>(Nb) * D * 2);                        // B bf16
     n += al256(static_cast<size_t>(Ma) * 4) + al256(static_cast<size_t>(Nb) * 4) + 256;   // norms, max
-    n += al256(static_cast<size_t>(sm_count()) * BM * TC_CAP * 8);      // per-CTA candidate lists
-    n += al256(static_cast<size_t>(Ma) * slices * KP_MAX * 8);          // published candidates
-    n += al256(static_cast<size_t>(Ma) * slices * 4);                   // t'
+    n += al256(static_cast<size_t>(sm_count()) * BM * kColHalves * TC_CAP * 8);   // per-CTA candidate lists
+    n += al256(static_cast<size_t>(Ma) * slices * kColHalves * KP_MAX * 8);       // published candidates
+    n += al256(static_cast<size_t>(Ma) * slices * kColHalves * 4);                // t'
     n += al256(static_cast<size_t>(Ma) * 4);                            // fallback row list
     n += rank_listed_workspace_bytes(D);                                // exact engine for uncertified rows
     return n;
@@ -749,11 +751,11 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     float *a_norm = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
     float *b_norm = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Nb) * 4);
     float *b_max = reinterpret_cast<float *>(ws); ws += 256;
-    uint64_t *cand_ws = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(sm_count()) * BM * TC_CAP * 8);
+    uint64_t *cand_ws = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(sm_count()) * BM * kColHalves * TC_CAP * 8);
     const int slices = tc_choose_slices(e.Ma, e.Nb);
-    uint64_t *cand_out = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * KP_MAX * 8);
+    uint64_t *cand_out = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * kColHalves * KP_MAX * 8);
     const int kp = e.K <= 24 ? 64 : 128;
-    float *tprime = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * 4);
+    float *tprime = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * kColHalves * 4);
     int32_t *fb_rows = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
     void *rank_ws = ws;
     const size_t rank_ws_bytes = workspace_bytes - static_cast<size_t>(ws - static_cast<unsigned char *>(workspace));
@@ -793,7 +795,7 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     }
 
     RescoreArgs r{};
-    r.A = e.A; r.B = e.B; r.Ma = e.Ma; r.Nb = e.Nb; r.D = e.d; r.K = e.K; r.n_slices = slices; r.kp = kp;
+    r.A = e.A; r.B = e.B; r.Ma = e.Ma; r.Nb = e.Nb; r.D = e.d; r.K = e.K; r.n_slices = slices * kColHalves; r.kp = kp;
     r.cand = cand_out; r.tprime = tprime; r.a_norm = a_norm; r.b_norm_max = b_max;
     // |bf16(x)-x| <= 2^-9|x| per operand -> products within (2^-8 + 2^-18) relative; tensor-core fp32
     // accumulation (assumed no worse than truncation per add) and the canonical chain's own rounding
