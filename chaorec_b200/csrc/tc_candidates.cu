@@ -149,25 +149,22 @@ __device__ __forceinline__ void warp_sort_desc_tc(uint64_t *s, int P, int lane) 
 // One 32-column chunk of one row: returns the new list length.
 __device__ __forceinline__ int filter_chunk(const uint32_t (&v)[32], float tau, uint32_t col0, uint32_t nb32, bool last_tile,
                                             uint64_t *row_buf, int cnt) {
-    float m[4];
+    float m[8];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const float a0 = fmaxf(fmaxf(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
-        const float a1 = fmaxf(fmaxf(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4])), __uint_as_float(v[8 * g + 5]));
-        const float a2 = fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
-        m[g] = fmaxf(fmaxf(a0, a1), a2);
-    }
-    const float mall = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+    for (int g = 0; g < 8; ++g)
+        m[g] = fmaxf(fmaxf(fmaxf(__uint_as_float(v[4 * g + 0]), __uint_as_float(v[4 * g + 1])), __uint_as_float(v[4 * g + 2])),
+                     __uint_as_float(v[4 * g + 3]));
+    const float mall = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
     if (mall > tau) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 8; ++g) {
             if (m[g] > tau) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float s = __uint_as_float(v[8 * g + j]);
+                for (int j = 0; j < 4; ++j) {
+                    const float s = __uint_as_float(v[4 * g + j]);
                     // (zero padding beyond Nb exists in the last tile only and is never listed)
-                    if (s > tau && (!last_tile || col0 + 8 * g + j < nb32)) {
-                        if (cnt < TC_CAP) row_buf[cnt] = make_key(s, col0 + 8 * g + j);
+                    if (s > tau && (!last_tile || col0 + 4 * g + j < nb32)) {
+                        if (cnt < TC_CAP) row_buf[cnt] = make_key(s, col0 + 4 * g + j);
                         ++cnt;
                     }
                 }
@@ -193,9 +190,12 @@ __device__ __forceinline__ void tc_select(uint64_t *row_buf, int n, int r, int l
         const int idx = lane + 32 * i;
         k[i] = (idx < n) ? row_buf[idx] : 0ull;
     }
+    // 18 of the 32 score bits are resolved: the threshold is then at most 2^-9 (relative) below the
+    // exact (r+1)-th score -- any lower bound is valid, it only keeps a few more entries -- and the
+    // search costs half as much (approximate scores carry 8 significant bits anyway)
     uint32_t prefix = 0;
 #pragma unroll 1
-    for (int b = 31; b >= 0; --b) {
+    for (int b = 31; b >= 14; --b) {
         const uint32_t cand = prefix | (1u << b);
         int c = 0;
 #pragma unroll
@@ -754,7 +754,9 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     uint64_t *cand_ws = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(sm_count()) * BM * kColHalves * TC_CAP * 8);
     const int slices = tc_choose_slices(e.Ma, e.Nb);
     uint64_t *cand_out = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * kColHalves * KP_MAX * 8);
-    const int kp = e.K <= 24 ? 64 : 128;
+    // K' = K + the candidates that can hide inside the certification window (a handful on
+    // Gaussian-like scores) + slack; uncertified rows fall back to the exact engine
+    const int kp = e.K <= 20 ? 32 : (e.K <= 50 ? 64 : 128);
     float *tprime = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * kColHalves * 4);
     int32_t *fb_rows = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
     void *rank_ws = ws;
