@@ -19,6 +19,7 @@ struct EngineArgs {
     int64_t id_offset;
     int64_t *out_idx;             // [Ma, K]
     float *out_score;             // nullable
+    int kp_hint;                  // tensor engine: K' (32, 64 or 128); 0 = choose from K
     const int32_t *row_list;      // nullable: process only rows row_list[0 .. *row_count_dev)
     const unsigned int *row_count_dev;
 };

@@ -676,6 +676,9 @@ extern "C" int chaorec_knn_cosine_topk(const float *feats, int64_t N, int32_t D,
     e.A = cn + row_lo * D; e.B = cn; e.Ma = row_hi - row_lo; e.Nb = N; e.d = D; e.K = k;
     e.mask_rowptr = nullptr; e.mask_col = nullptr; e.mask_value = 0.0f;
     e.exclude_self = exclude_self ? 1 : 0; e.self_off = row_lo; e.id_offset = 0;
+    // cosine similarities of CNN-like (non-negative) features are tightly packed: a wider candidate
+    // list keeps the certification rate high (225 of 23,033 rows uncertified at K'=64, 16,513 at 32)
+    e.kp_hint = (k <= 16) ? 64 : 128;
     e.out_idx = out_idx; e.out_score = out_val;
     const size_t left = workspace_bytes - static_cast<size_t>(ws - reinterpret_cast<unsigned char *>(workspace));
     if (use_tensor_engine(e.Ma, N, D, k)) return tc_topk_launch(e, ws, left, stm);

@@ -25,6 +25,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "engine.cuh"
 
@@ -756,7 +758,13 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     uint64_t *cand_out = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * kColHalves * KP_MAX * 8);
     // K' = K + the candidates that can hide inside the certification window (a handful on
     // Gaussian-like scores) + slack; uncertified rows fall back to the exact engine
-    const int kp = e.K <= 20 ? 32 : (e.K <= 50 ? 64 : 128);
+    int kp = e.K <= 20 ? 32 : (e.K <= 50 ? 64 : 128);
+    if (e.kp_hint == 32 || e.kp_hint == 64 || e.kp_hint == 128) kp = e.kp_hint;
+    if (const char *env = getenv("CHAOREC_TC_KP")) {
+        const int v = atoi(env);
+        if (v == 32 || v == 64 || v == 128) kp = v;
+    }
+    if (kp < e.K + 8) kp = (e.K + 8 <= 64) ? 64 : 128;
     float *tprime = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * kColHalves * 4);
     int32_t *fb_rows = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
     void *rank_ws = ws;
