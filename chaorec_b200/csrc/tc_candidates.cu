@@ -122,7 +122,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // back-off wait for the long, latency-insensitive waits of the single-lane producer / MMA roles
 // (a tight try_wait loop steals issue slots from the epilogue warps on the same scheduler)
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // suspend-time hint (ns)
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+    }
 }
 
 __device__ __forceinline__ uint64_t smem_desc(const void *p) {
@@ -148,9 +159,19 @@ __device__ __forceinline__ void warp_sort_desc_tc(uint64_t *s, int P, int lane) 
     }
 }
 
-// One 32-column chunk of one row: returns the new list length.
-__device__ __forceinline__ int filter_chunk(const uint32_t (&v)[32], float tau, uint32_t col0, uint32_t nb32, bool last_tile,
-                                            uint64_t *row_buf, int cnt) {
+// List entries are stored RAW while a unit runs: (score bits << 32) | column -- one 64-bit store of
+// a register pair, no ALU work; orderable keys are formed only when a list is compacted or sorted.
+__device__ __forceinline__ uint64_t raw_entry(float s, uint32_t col) {
+    return (static_cast<uint64_t>(__float_as_uint(s)) << 32) | col;
+}
+__device__ __forceinline__ uint64_t key_of_raw(uint64_t raw) {
+    return make_key(__uint_as_float(static_cast<uint32_t>(raw >> 32)), static_cast<uint32_t>(raw & 0xFFFFFFFFull));
+}
+__device__ __forceinline__ uint64_t raw_of_key(uint64_t key) { return raw_entry(key_score(key), key_index(key)); }
+
+// One 32-column chunk of one row.  `wr` is the row's append cursor (the list cannot overflow: a
+// tile adds at most 64 entries and lists are compacted before they get within 64 of the capacity).
+__device__ __forceinline__ uint64_t *filter_chunk(const uint32_t (&v)[32], float tau, uint32_t col0, uint64_t *wr) {
     float m[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g)
@@ -164,16 +185,20 @@ __device__ __forceinline__ int filter_chunk(const uint32_t (&v)[32], float tau, 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float s = __uint_as_float(v[4 * g + j]);
-                    // (zero padding beyond Nb exists in the last tile only and is never listed)
-                    if (s > tau && (!last_tile || col0 + 4 * g + j < nb32)) {
-                        if (cnt < TC_CAP) row_buf[cnt] = make_key(s, col0 + 4 * g + j);
-                        ++cnt;
-                    }
+                    if (s > tau) *wr++ = raw_entry(s, col0 + 4 * g + j);
                 }
             }
         }
     }
-    return cnt;
+    return wr;
+}
+
+// Zero padding beyond Nb exists in the last column tile only: those accumulator values are
+// replaced by -inf before filtering, so the per-column path needs no bound check.
+__device__ __forceinline__ void mask_padding(uint32_t (&v)[32], uint32_t col0, uint32_t nb32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+        if (col0 + j >= nb32) v[j] = 0xFF800000u;   // -inf
 }
 
 constexpr int kKeysPerLane = TC_CAP / 32;
@@ -190,7 +215,7 @@ __device__ __forceinline__ void tc_select(uint64_t *row_buf, int n, int r, int l
 #pragma unroll
     for (int i = 0; i < kKeysPerLane; ++i) {
         const int idx = lane + 32 * i;
-        k[i] = (idx < n) ? row_buf[idx] : 0ull;
+        k[i] = (idx < n) ? key_of_raw(row_buf[idx]) : 0ull;
     }
     // 18 of the 32 score bits are resolved: the threshold is then at most 2^-9 (relative) below the
     // exact (r+1)-th score -- any lower bound is valid, it only keeps a few more entries -- and the
@@ -219,7 +244,7 @@ __device__ __forceinline__ void tc_select(uint64_t *row_buf, int n, int r, int l
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < kKeysPerLane; ++i) {
-        if (k[i] != 0ull && static_cast<uint32_t>(k[i] >> 32) >= prefix) row_buf[pos++] = k[i];
+        if (k[i] != 0ull && static_cast<uint32_t>(k[i] >> 32) >= prefix) row_buf[pos++] = raw_of_key(k[i]);
     }
     __syncwarp();
     new_cnt = total;
@@ -234,7 +259,7 @@ __device__ __forceinline__ void tc_finish(const TcArgs *__restrict__ a, int64_t 
                                           uint64_t *scratch, int lane, int KP, float old_tau, int &kept_out, float &tprime) {
     int P = 64;
     while (P < n) P <<= 1;
-    for (int t = lane; t < P; t += 32) scratch[t] = (t < n) ? row_buf[t] : 0ull;
+    for (int t = lane; t < P; t += 32) scratch[t] = (t < n) ? key_of_raw(row_buf[t]) : 0ull;
     __syncwarp();
     warp_sort_desc_tc(scratch, P, lane);
     int64_t m_lo = 0;
@@ -421,6 +446,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             bool give_up = row_ok && (r_keep + 32 > kTcTrigger);
             float tau = (row_ok && !give_up) ? -INFINITY : INFINITY;
             int cnt = 0;
+            uint64_t *wr = row_buf;
             for (int t = t_lo; t < t_hi; ++t) {
                 mbar_wait(&tfull_bar[as], aphase);
                 tc_fence_after();
@@ -437,9 +463,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 tmem_ld_wait();
                 __syncwarp();
                 tmem_ld32(taddr + ch * 64 + 32, vb);
-                cnt = filter_chunk(va, tau, tcol, nb32, last_tile, row_buf, cnt);
+                if (last_tile) mask_padding(va, tcol, nb32);
+                wr = filter_chunk(va, tau, tcol, wr);
                 tmem_ld_wait();
-                cnt = filter_chunk(vb, tau, tcol + 32, nb32, last_tile, row_buf, cnt);
+                if (last_tile) mask_padding(vb, tcol + 32, nb32);
+                wr = filter_chunk(vb, tau, tcol + 32, wr);
+                cnt = static_cast<int>(wr - row_buf);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[as]);      // this warp is done with the stage
@@ -462,7 +491,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     float nt;
                     tc_select(buf_src, n_src < TC_CAP ? n_src : TC_CAP, r_src, lane, nc, nt);
                     if (lane == src) {
-                        if (n_src > TC_CAP || nc > kTcTrigger) {  // overflowed, or a huge run of exact ties
+                        if (n_src > TC_CAP || nc > kTcTrigger) {  // (cannot overflow) / a huge run of exact ties
                             give_up = true;
                             tau = INFINITY;
                             cnt = 0;
@@ -470,6 +499,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                             cnt = nc;
                             tau = nt;
                         }
+                        wr = row_buf + cnt;
                     }
                 }
             }
