@@ -22,6 +22,10 @@ struct EngineArgs {
     int kp_hint;                  // tensor engine: K' (32, 64 or 128); 0 = choose from K
     const int32_t *row_list;      // nullable: process only rows row_list[0 .. *row_count_dev)
     const unsigned int *row_count_dev;
+    // row-list mode: seed_keys[p] (nullable) is a key the p-th listed row is known to reach with K
+    // columns (the exact K-th best among its re-scored candidates): the scan then starts with that
+    // threshold instead of -inf and lists only the handful of columns that can still matter
+    const uint64_t *seed_keys;
 };
 
 // exact fp32 CUDA-core engine (rank_topk.cu)

@@ -69,6 +69,7 @@ struct RankArgs {
     int n_col_slices;                   // 1 = off
     int tiles_per_slice;
     uint64_t *slice_out;                // [kSliceCapRows][n_col_slices][K]
+    const uint64_t *seed_keys;          // nullable, row-list mode: initial threshold of every listed row
     int run_if_count_le;                // listed launches: run only if count <= this (sliced) ...
     int run_if_count_gt;                // ... or only if count > this (unsliced sibling); -1 = always
 };
@@ -329,14 +330,23 @@ __global__ void __launch_bounds__(kThreads, A_RESIDENT ? 2 : 1) rank_topk_kernel
 
     for (;;) {
         if (tid == 0) *s_tile = static_cast<int>(atomicAdd(a.tile_counter, 1u));
-        if (tid < TU) {
-            st->tau_f[tid] = -INFINITY;
-            st->cnt[tid] = 0;
-            st->tau_key[tid] = 0ull;
-        }
         __syncthreads();
         const int ut = *s_tile;
         if (ut >= n_row_tiles) break;
+        if (tid < TU) {
+            float tf = -INFINITY;
+            uint64_t tk = 0ull;
+            if (a.seed_keys != nullptr) {
+                const int64_t p = static_cast<int64_t>(ut / S) * TU + tid;
+                if (p < Ma_eff) {
+                    const uint64_t seed = a.seed_keys[p];
+                    if (seed != 0ull) { tk = seed - 1ull; tf = key_score(seed); }   // keep everything >= seed
+                }
+            }
+            st->tau_f[tid] = tf;
+            st->cnt[tid] = 0;
+            st->tau_key[tid] = tk;
+        }
         const int sl = ut % S;
         const int it_lo = (S > 1) ? sl * a.tiles_per_slice : 0;
         const int it_hi = (S > 1) ? ((it_lo + a.tiles_per_slice < n_it) ? it_lo + a.tiles_per_slice : n_it) : n_it;
@@ -514,7 +524,7 @@ int rank_launch_engine(const EngineArgs &e, void *workspace, size_t workspace_by
     a.mask_rowptr = e.mask_rowptr; a.mask_col = e.mask_col; a.mask_value = e.mask_value;
     a.exclude_self = e.exclude_self; a.self_off = e.self_off; a.id_offset = e.id_offset;
     a.out_idx = e.out_idx; a.out_score = e.out_score;
-    a.row_list = e.row_list; a.row_count_dev = e.row_count_dev;
+    a.row_list = e.row_list; a.row_count_dev = e.row_count_dev; a.seed_keys = e.seed_keys;
     a.n_col_slices = 1; a.tiles_per_slice = 0; a.slice_out = nullptr;
     a.run_if_count_le = -1; a.run_if_count_gt = -1;
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return CHAOREC_E_ALIGN;

@@ -603,6 +603,7 @@ struct RescoreArgs {
     int64_t *out_idx;
     float *out_score;
     int32_t *fallback_rows;    // rows whose exact top-K could not be certified
+    uint64_t *fallback_seeds;  // their exact K-th best key so far (0 if fewer than K entries)
     unsigned int *fallback_count;
 };
 
@@ -703,6 +704,7 @@ __global__ void __launch_bounds__(kRescoreWarps * 32) rescore_kernel(const Resco
     } else if (lane == 0) {
         const unsigned slot = atomicAdd(a.fallback_count, 1u);
         a.fallback_rows[slot] = static_cast<int32_t>(row);
+        a.fallback_seeds[slot] = kth;
     }
 }
 
@@ -764,6 +766,7 @@ size_t tc_workspace_bytes(int64_t Ma, int64_t Nb, int D) {
     n += al256(static_cast<size_t>(Ma) * slices * kColHalves * KP_MAX * 8);       // published candidates
     n += al256(static_cast<size_t>(Ma) * slices * kColHalves * 4);                // t'
     n += al256(static_cast<size_t>(Ma) * 4);                            // fallback row list
+    n += al256(static_cast<size_t>(Ma) * 8);                            // ... and their seed keys
     n += rank_listed_workspace_bytes(D);                                // exact engine for uncertified rows
     return n;
 }
@@ -797,6 +800,7 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     if (kp < e.K + 8) kp = (e.K + 8 <= 64) ? 64 : 128;
     float *tprime = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * kColHalves * 4);
     int32_t *fb_rows = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
+    uint64_t *fb_seeds = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 8);
     void *rank_ws = ws;
     const size_t rank_ws_bytes = workspace_bytes - static_cast<size_t>(ws - static_cast<unsigned char *>(workspace));
 
@@ -843,7 +847,7 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     r.gamma = 0.00390625f * 1.01f + 3.0f * static_cast<float>(e.d) * 5.9604645e-8f;
     r.mask_rowptr = e.mask_rowptr; r.mask_col = e.mask_col; r.mask_value = e.mask_value;
     r.id_offset = e.id_offset; r.out_idx = e.out_idx; r.out_score = e.out_score;
-    r.fallback_rows = fb_rows; r.fallback_count = counters + 16;
+    r.fallback_rows = fb_rows; r.fallback_seeds = fb_seeds; r.fallback_count = counters + 16;
     rescore_kernel<<<static_cast<unsigned>((e.Ma + kRescoreWarps - 1) / kRescoreWarps), kRescoreWarps * 32, 0, stm>>>(r);
     int rc = launch_status();
     if (rc != CHAOREC_OK) return rc;
@@ -851,6 +855,7 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     EngineArgs fb = e;
     fb.row_list = fb_rows;
     fb.row_count_dev = counters + 16;
+    fb.seed_keys = fb_seeds;
     return rank_launch_engine(fb, rank_ws, rank_ws_bytes, stm);
 }
 

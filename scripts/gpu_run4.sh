@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 tail -6 gpurun_out/pytest_gpu.log
 (timeout 900 python bench.py --steps 3 --warmup 3) > gpurun_out/bench4.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench4.log
 tail -3 gpurun_out/bench4.log
-KREG='regex:rank_topk|spmm_|topk_hits|row_norm|row_scale|tc_cand|rescore|to_bf16|max_reduce'
+KREG='regex:rank_topk|spmm_|topk_hits|row_norm|row_scale|tc_cand|rescore|to_bf16|max_reduce|slice_merge'
 (timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -c 300 --csv --log-file gpurun_out/launches_r01b.csv python bench.py --steps 2 --warmup 1 --legs eval,knn) > gpurun_out/ncu_launches.log 2>&1
 python - <<'PY'
 import csv, collections
