@@ -169,6 +169,25 @@ __device__ __forceinline__ uint64_t key_of_raw(uint64_t raw) {
 }
 __device__ __forceinline__ uint64_t raw_of_key(uint64_t key) { return raw_entry(key_score(key), key_index(key)); }
 
+// Branch-free conditional append: setp + predicated 64-bit store + selp.  (Written as `if (s > tau)
+// *wr++ = ...` the compiler emits a branch per column; the epilogue then stalls on branch
+// resolution and fixed-latency predicate dependencies -- 40 % of its issue slots in the ncu
+// captures under profiles/.)
+__device__ __forceinline__ uint64_t *append_if_above(uint64_t *wr, float s, float tau, uint32_t col) {
+    uint32_t inc;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.gt.f32 p, %2, %3;\n\t"
+        "@p st.global.v2.u32 [%1], {%4, %5};\n\t"
+        "selp.u32 %0, 8, 0, p;\n\t"
+        "}"
+        : "=r"(inc)
+        : "l"(wr), "f"(s), "f"(tau), "r"(col), "r"(__float_as_uint(s))
+        : "memory");
+    return reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(wr) + inc);
+}
+
 // One 32-column chunk of one row.  `wr` is the row's append cursor (the list cannot overflow: a
 // tile adds at most 64 entries and lists are compacted before they get within 64 of the capacity).
 __device__ __forceinline__ uint64_t *filter_chunk(const uint32_t (&v)[32], float tau, uint32_t col0, uint64_t *wr) {
@@ -183,10 +202,7 @@ __device__ __forceinline__ uint64_t *filter_chunk(const uint32_t (&v)[32], float
         for (int g = 0; g < 8; ++g) {
             if (m[g] > tau) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float s = __uint_as_float(v[4 * g + j]);
-                    if (s > tau) *wr++ = raw_entry(s, col0 + 4 * g + j);
-                }
+                for (int j = 0; j < 4; ++j) wr = append_if_above(wr, __uint_as_float(v[4 * g + j]), tau, col0 + 4 * g + j);
             }
         }
     }
