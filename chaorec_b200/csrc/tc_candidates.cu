@@ -63,6 +63,7 @@ struct TcArgs {
     int D;
     int n_row_tiles, n_slices, tiles_per_slice;   // tiles = BN-column tiles
     int kp;                                        // K': candidates kept per (row, slice)
+    int debug_mode;                                // CHAOREC_TC_DEBUG: 1 = no row ever passes the filter, 2 = epilogue skips TMEM loads (timing experiments only; every row then falls back to the exact engine)
     const int64_t *mask_rowptr;
     const int32_t *mask_col;
     int exclude_self;
@@ -459,7 +460,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
             // a row whose kept set could not leave room for a tile of appends (a user with hundreds of
             // train items) is not pre-filtered at all: it goes to the exact engine
-            bool give_up = row_ok && (r_keep + 32 > kTcTrigger);
+            bool give_up = row_ok && ((r_keep + 32 > kTcTrigger) || a.debug_mode != 0);
             float tau = (row_ok && !give_up) ? -INFINITY : INFINITY;
             int cnt = 0;
             uint64_t *wr = row_buf;
@@ -475,6 +476,13 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const uint32_t tcol = static_cast<uint32_t>(t) * BN + ch * 64;
                 uint32_t va[32], vb[32];
                 __syncwarp();
+                if (a.debug_mode == 2) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                    if (++as == 2) { as = 0; aphase ^= 1u; }
+                    continue;
+                }
                 tmem_ld32(taddr + ch * 64, va);
                 tmem_ld_wait();
                 __syncwarp();
@@ -839,6 +847,7 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     t.mask_rowptr = e.mask_rowptr; t.mask_col = e.mask_col;
     t.exclude_self = e.exclude_self; t.self_off = e.self_off;
     t.cand_ws = cand_ws; t.cand_out = cand_out; t.tprime_out = tprime; t.kp = kp;
+    if (const char *dbg = getenv("CHAOREC_TC_DEBUG")) t.debug_mode = atoi(dbg);
     const int n_units = t.n_row_tiles * slices;
     const int grid = n_units < sm_count() ? n_units : sm_count();
     cudaError_t ce;
