@@ -33,29 +33,34 @@
 namespace chaorec {
 namespace {
 
-constexpr int BM = 256;          // rows of A per unit (two MMA halves of 128)
-constexpr int BN = 128;          // columns per accumulator tile
 constexpr int BK = 64;           // bf16 elements per pipeline stage (= one 128-byte swizzle row)
-constexpr int kABytes = BM * BK * 2;   // 32 KB
-constexpr int kBBytes = BN * BK * 2;   // 16 KB
-// Two pipeline shapes.  D > 64: every stage carries a K-slab of A and of B (3 x 48 KB).  D <= 64
-// (the evaluation path, one K-slab in total): the A slab is loaded once per unit and stays
-// resident, the ring carries B slabs only (6 x 16 KB) -> a third of the L2->SM traffic per tile
-// and twice as many loads in flight.
-template <bool A_RES> struct Pipe {
-    static constexpr int kStages = A_RES ? 6 : 3;
+// Two tile shapes, 32768 scores per accumulator tile and 512 TMEM columns (2 stages) in both:
+//   d > 64 : 256 rows (2 MMA blocks of 128) x 128 columns; every ring stage carries a K-slab of A and
+//            of B (3 x 48 KB); two epilogue threads per row, one per 64-column half -> 2 lists per row.
+//   d <= 64: 512 rows (4 MMA blocks) x 64 columns; the single K-slab of A is loaded once per unit and
+//            stays resident (64 KB), the ring carries B slabs only (8 x 8 KB) -> half the L2->SM
+//            traffic per score, one epilogue thread and ONE list per row (half the list upkeep).
+template <bool A_RES> struct Shape {
+    static constexpr int RB = A_RES ? 4 : 2;                 // 128-row MMA blocks per unit
+    static constexpr int BM = RB * 128;                      // rows of A per unit
+    static constexpr int BN = A_RES ? 64 : 128;              // columns per accumulator tile
+    static constexpr int CH = BN / 64;                       // 64-column shares per tile = lists per row
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStages = A_RES ? 8 : 3;
     static constexpr int kStageBytes = A_RES ? kBBytes : (kABytes + kBBytes);
     static constexpr int kRingOff = A_RES ? kABytes : 0;
     static constexpr int kRingBytes = kRingOff + kStages * kStageBytes;
-    static constexpr int kNumBars = 2 * kStages + 4 + 2;   // full/empty ring, tmem full/empty x2, A full/empty
+    static constexpr int kNumBars = 2 * kStages + 4 + 2;     // full/empty ring, tmem full/empty x2, A full/empty
+    // tcgen05 instruction descriptor: F32 accumulate, BF16 x BF16, K-major A and B, N = BN, M = 128
+    static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((static_cast<uint32_t>(BN) >> 3) << 17) | ((128u >> 4) << 24);
 };
+constexpr int kBoxRowsA = 256;    // TMA box height of the A map (the hardware limit)
 constexpr int kTcThreads = 576;   // 2 role warps + 16 epilogue warps
 constexpr int kEpiWarps = 16;
-constexpr int kColHalves = 2;     // two epilogue threads per row, one per 64-column half of every tile
 constexpr int TC_CAP = 256;      // candidate slots per (row, column half) list inside a unit
-constexpr int kTcTrigger = TC_CAP - BN / kColHalves;   // a tile adds at most 64 entries to a list
+constexpr int kTcTrigger = TC_CAP - 64;   // a tile adds at most 64 entries to a list
 constexpr int KP_MAX = 128;      // K' (approximate candidates kept per (row, slice)) is 64 or 128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO=1024 B, version 1, SWIZZLE_128B
 
 struct TcArgs {
@@ -68,9 +73,9 @@ struct TcArgs {
     const int32_t *mask_col;
     int exclude_self;
     int64_t self_off;
-    uint64_t *cand_ws;        // [gridDim.x][BM][kColHalves][TC_CAP]
-    uint64_t *cand_out;       // [Ma][n_slices*kColHalves][KP] approximate keys, best first (0 = empty)
-    float *tprime_out;        // [Ma][n_slices*kColHalves] approx score of the KP-th kept candidate (-inf: list complete)
+    uint64_t *cand_ws;        // [gridDim.x][BM][CH][TC_CAP]
+    uint64_t *cand_out;       // [Ma][n_slices*CH][KP] approximate keys, best first (0 = empty)
+    float *tprime_out;        // [Ma][n_slices*CH] approx score of the KP-th kept candidate (-inf: list complete)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -317,13 +322,16 @@ __device__ __forceinline__ void tc_finish(const TcArgs *__restrict__ a, int64_t 
 template <bool A_RES>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcArgs a) {
-    constexpr int kStages = Pipe<A_RES>::kStages;
-    constexpr int kStageBytes = Pipe<A_RES>::kStageBytes;
+    using S = Shape<A_RES>;
+    constexpr int kStages = S::kStages;
+    constexpr int kStageBytes = S::kStageBytes;
+    constexpr int BM = S::BM, BN = S::BN, RB = S::RB, CH = S::CH;
+    constexpr int kABytes = S::kABytes;
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     // layout: [resident A slab (A_RES)] [ring stages] [sort scratch 8 x 4 KB] [barriers] [tmem base] [args]
     unsigned char *a_res = tc_smem;
-    unsigned char *stages = tc_smem + Pipe<A_RES>::kRingOff;
-    uint64_t *scratch_all = reinterpret_cast<uint64_t *>(tc_smem + Pipe<A_RES>::kRingBytes);
+    unsigned char *stages = tc_smem + S::kRingOff;
+    uint64_t *scratch_all = reinterpret_cast<uint64_t *>(tc_smem + S::kRingBytes);
     uint64_t *bars = scratch_all + kEpiWarps * TC_CAP;
     uint64_t *full_bar = bars;                    // [kStages]
     uint64_t *empty_bar = bars + kStages;         // [kStages]
@@ -331,7 +339,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint64_t *tempty_bar = bars + 2 * kStages + 2;  // [2]
     uint64_t *afull_bar = bars + 2 * kStages + 4;   // resident A slab landed
     uint64_t *aempty_bar = bars + 2 * kStages + 5;  // every MMA reading the resident A slab retired
-    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + Pipe<A_RES>::kNumBars);
+    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + S::kNumBars);
     TcArgs *s_args = reinterpret_cast<TcArgs *>(tmem_base_smem + 4);
 
     const int warp = threadIdx.x >> 5;
@@ -373,7 +381,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 if (A_RES) {
                     mbar_wait_backoff(aempty_bar, uphase ^ 1u);   // previous unit's MMAs are done with the slab
                     mbar_arrive_expect_tx(afull_bar, kABytes);
-                    tma_load_2d(a_res, &map_a, 0, rt * BM, afull_bar);
+                    for (int i = 0; i < BM / kBoxRowsA; ++i)
+                        tma_load_2d(a_res + i * kBoxRowsA * BK * 2, &map_a, 0, rt * BM + i * kBoxRowsA, afull_bar);
                     uphase ^= 1u;
                 }
                 for (int t = t_lo; t < t_hi; ++t) {
@@ -412,15 +421,18 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         tc_fence_after();
                         const unsigned char *sa = stages + stage * kStageBytes;
                         const unsigned char *pa = A_RES ? a_res : sa;
-                        const uint64_t da0 = smem_desc(pa);
-                        const uint64_t da1 = smem_desc(pa + 128 * BK * 2);
+                        const uint64_t da = smem_desc(pa);
                         const uint64_t db = smem_desc(sa + (A_RES ? 0 : kABytes));
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint32_t acc = (kc > 0 || k > 0) ? 1u : 0u;
-                            // +32 bytes along K inside the 128-byte swizzle row = +2 in the (>>4) address field
-                            umma_bf16(tmem_base + (as * 2 + 0) * BN, da0 + 2 * k, db + 2 * k, kIdesc, acc);
-                            umma_bf16(tmem_base + (as * 2 + 1) * BN, da1 + 2 * k, db + 2 * k, kIdesc, acc);
+#pragma unroll
+                            for (int rb = 0; rb < RB; ++rb) {
+                                // +32 bytes along K inside the 128-byte swizzle row = +2 in the (>>4) address field;
+                                // the next 128-row block of A starts 16 KB (= 1024 in that field) further
+                                umma_bf16(tmem_base + (as * RB + rb) * BN, da + rb * (128 * BK * 2 / 16) + 2 * k, db + 2 * k,
+                                          S::kIdesc, acc);
+                            }
                         }
                         umma_commit(&empty_bar[stage]);           // smem stage reusable once these MMAs retire
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -435,15 +447,15 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // ================= epilogue: one thread per row =================
         const int ew = warp - 2;                 // 0..15
         const int q = warp & 3;                  // TMEM lane quadrant this warp may access
-        const int h = (ew >> 2) & 1;             // which 128-row half
-        const int ch = ew >> 3;                  // which 64-column half of every tile
-        const int row_local = h * 128 + q * 32 + lane;
+        const int rb = (ew >> 2) % RB;           // which 128-row block of the unit
+        const int ch = (ew >> 2) / RB;           // which 64-column share of every tile (always 0 when BN == 64)
+        const int row_local = rb * 128 + q * 32 + lane;
         uint64_t *scratch = scratch_all + ew * TC_CAP;
-        const size_t list0 = (static_cast<size_t>(blockIdx.x) * BM + (row_local - lane)) * kColHalves + ch;   // lane 0's list
-        uint64_t *row_buf = a.cand_ws + (list0 + static_cast<size_t>(lane) * kColHalves) * TC_CAP;
+        const size_t list0 = (static_cast<size_t>(blockIdx.x) * BM + (row_local - lane)) * CH + ch;   // lane 0's list
+        uint64_t *row_buf = a.cand_ws + (list0 + static_cast<size_t>(lane) * CH) * TC_CAP;
         int as = 0;
         uint32_t aphase = 0;
-        const int n_lists = a.n_slices * kColHalves;
+        const int n_lists = a.n_slices * CH;
         const int KP = a.kp;
         const uint32_t nb32 = static_cast<uint32_t>(a.Nb);
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -467,7 +479,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             for (int t = t_lo; t < t_hi; ++t) {
                 mbar_wait(&tfull_bar[as], aphase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * 2 + h) * BN;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * RB + rb) * BN;
                 // 32-column chunks, software-pipelined: the next chunk's tcgen05.ld is in flight while the
                 // current one is filtered.  Filter = maxima of the four 8-column groups (independent
                 // FMNMX3 trees), one combined test, then only the groups in which this row beats its
@@ -510,7 +522,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     need &= need - 1;
                     const int n_src = __shfl_sync(0xffffffffu, cnt, src);
                     const int r_src = __shfl_sync(0xffffffffu, r_keep, src);
-                    uint64_t *buf_src = a.cand_ws + (list0 + static_cast<size_t>(src) * kColHalves) * TC_CAP;
+                    uint64_t *buf_src = a.cand_ws + (list0 + static_cast<size_t>(src) * CH) * TC_CAP;
                     int nc;
                     float nt;
                     tc_select(buf_src, n_src < TC_CAP ? n_src : TC_CAP, r_src, lane, nc, nt);
@@ -536,12 +548,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int gu_src = __shfl_sync(0xffffffffu, give_up ? 1 : 0, src);
                 const int64_t row_src = row - lane + src;
                 if (row_src >= a.Ma) continue;                    // warp-uniform
-                const int list_id = sl * kColHalves + ch;
+                const int list_id = sl * CH + ch;
                 uint64_t *out = a.cand_out + (static_cast<size_t>(row_src) * n_lists + list_id) * KP;
                 float tp = INFINITY;                              // +inf: cannot be certified -> exact engine
                 int nc = 0;
                 if (!gu_src && n_src <= TC_CAP) {
-                    uint64_t *buf_src = a.cand_ws + (list0 + static_cast<size_t>(src) * kColHalves) * TC_CAP;
+                    uint64_t *buf_src = a.cand_ws + (list0 + static_cast<size_t>(src) * CH) * TC_CAP;
                     if (n_src > r_src + 1) {                      // cut to the r_keep best before sorting
                         float nt;
                         tc_select(buf_src, n_src, r_src, lane, n_src, nt);
@@ -567,8 +579,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
 template <bool A_RES>
 constexpr size_t tc_smem_bytes() {
-    return static_cast<size_t>(Pipe<A_RES>::kRingBytes) + static_cast<size_t>(kEpiWarps) * TC_CAP * 8 +
-           Pipe<A_RES>::kNumBars * 8 + 16 + sizeof(TcArgs) + 64;
+    return static_cast<size_t>(Shape<A_RES>::kRingBytes) + static_cast<size_t>(kEpiWarps) * TC_CAP * 8 +
+           Shape<A_RES>::kNumBars * 8 + 16 + sizeof(TcArgs) + 64;
 }
 
 // ---- fp32 -> bf16 operand copies (+ row norms for the error bound) ------------------------------
@@ -769,26 +781,34 @@ size_t al256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
 // -------------------------------------------------------------------------------------------------
 // Host orchestration shared by the eval and kNN entry points.
 // -------------------------------------------------------------------------------------------------
-int tc_choose_slices(int64_t Ma, int64_t Nb) {
-    const int row_tiles = static_cast<int>((Ma + BM - 1) / BM);
-    const int col_tiles = static_cast<int>((Nb + BN - 1) / BN);
+struct HostShape { int BM, BN, CH; };
+static HostShape host_shape(int D) {
+    return D <= BK ? HostShape{Shape<true>::BM, Shape<true>::BN, Shape<true>::CH}
+                   : HostShape{Shape<false>::BM, Shape<false>::BN, Shape<false>::CH};
+}
+
+int tc_choose_slices(int64_t Ma, int64_t Nb, int D) {
+    const HostShape hs = host_shape(D);
+    const int row_tiles = static_cast<int>((Ma + hs.BM - 1) / hs.BM);
+    const int col_tiles = static_cast<int>((Nb + hs.BN - 1) / hs.BN);
     const int sms = sm_count();
     int slices = 1;
     // enough units to balance the persistent grid (>= 4 waves of work items), at most 4 slices so
-    // that n_slices*KP + K candidates fit the re-score buffer
+    // that n_lists * K' + K candidates fit the re-score buffer
     while (slices < 4 && row_tiles * slices < 4 * sms && col_tiles / (slices * 2) >= 8) slices *= 2;
     return slices;
 }
 
 size_t tc_workspace_bytes(int64_t Ma, int64_t Nb, int D) {
-    const int slices = tc_choose_slices(Ma, Nb);
+    const HostShape hs = host_shape(D);
+    const int slices = tc_choose_slices(Ma, Nb, D);
     size_t n = 256;                                                    // counters
     n += al256(static_cast<size_t>(Ma) * D * 2);                        // A bf16
     n += al256(static_cast<size_t>(Nb) * D * 2);                        // B bf16
     n += al256(static_cast<size_t>(Ma) * 4) + al256(static_cast<size_t>(Nb) * 4) + 256;   // norms, max
-    n += al256(static_cast<size_t>(sm_count()) * BM * kColHalves * TC_CAP * 8);   // per-CTA candidate lists
-    n += al256(static_cast<size_t>(Ma) * slices * kColHalves * KP_MAX * 8);       // published candidates
-    n += al256(static_cast<size_t>(Ma) * slices * kColHalves * 4);                // t'
+    n += al256(static_cast<size_t>(sm_count()) * hs.BM * hs.CH * TC_CAP * 8);   // per-CTA candidate lists
+    n += al256(static_cast<size_t>(Ma) * slices * hs.CH * KP_MAX * 8);          // published candidates
+    n += al256(static_cast<size_t>(Ma) * slices * hs.CH * 4);                   // t'
     n += al256(static_cast<size_t>(Ma) * 4);                            // fallback row list
     n += al256(static_cast<size_t>(Ma) * 8);                            // ... and their seed keys
     n += rank_listed_workspace_bytes(D);                                // exact engine for uncertified rows
@@ -797,7 +817,7 @@ size_t tc_workspace_bytes(int64_t Ma, int64_t Nb, int D) {
 
 bool tc_supported(int64_t Ma, int64_t Nb, int D, int K) {
     // small problems stay on the exact engine (nothing to win, and K' must be well below Nb)
-    return D % 8 == 0 && D >= 8 && K >= 1 && K <= 64 && Nb >= 8 * BN && Ma >= 1 && Ma < 0x7FFFFFF0LL && encode_fn() != nullptr;
+    return D % 8 == 0 && D >= 8 && K >= 1 && K <= 64 && Nb >= 1024 && Ma >= 1 && Ma < 0x7FFFFFF0LL && encode_fn() != nullptr;
 }
 
 // A, B: fp32 operands (same pointer allowed).  Computes exact canonical top-K of every row of A.
@@ -810,9 +830,10 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     float *a_norm = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
     float *b_norm = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Nb) * 4);
     float *b_max = reinterpret_cast<float *>(ws); ws += 256;
-    uint64_t *cand_ws = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(sm_count()) * BM * kColHalves * TC_CAP * 8);
-    const int slices = tc_choose_slices(e.Ma, e.Nb);
-    uint64_t *cand_out = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * kColHalves * KP_MAX * 8);
+    const HostShape hs = host_shape(e.d);
+    uint64_t *cand_ws = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(sm_count()) * hs.BM * hs.CH * TC_CAP * 8);
+    const int slices = tc_choose_slices(e.Ma, e.Nb, e.d);
+    uint64_t *cand_out = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * hs.CH * KP_MAX * 8);
     // K' = K + the candidates that can hide inside the certification window (a handful on
     // Gaussian-like scores) + slack; uncertified rows fall back to the exact engine
     int kp = e.K <= 20 ? 32 : (e.K <= 50 ? 64 : 128);
@@ -822,7 +843,7 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
         if (v == 32 || v == 64 || v == 128) kp = v;
     }
     if (kp < e.K + 8) kp = (e.K + 8 <= 64) ? 64 : 128;
-    float *tprime = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * kColHalves * 4);
+    float *tprime = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * hs.CH * 4);
     int32_t *fb_rows = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
     uint64_t *fb_seeds = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 8);
     void *rank_ws = ws;
@@ -836,13 +857,13 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
         max_reduce_kernel<<<1, 1024, 0, stm>>>(b_norm, e.Nb, b_max);
     }
     CUtensorMap map_a, map_b;
-    if (!make_map(&map_a, a16, e.Ma, e.d, BM) || !make_map(&map_b, b16, e.Nb, e.d, BN)) return CHAOREC_E_LAUNCH;
+    if (!make_map(&map_a, a16, e.Ma, e.d, kBoxRowsA) || !make_map(&map_b, b16, e.Nb, e.d, hs.BN)) return CHAOREC_E_LAUNCH;
 
     TcArgs t{};
     t.Ma = e.Ma; t.Nb = e.Nb; t.D = e.d;
-    t.n_row_tiles = static_cast<int>((e.Ma + BM - 1) / BM);
+    t.n_row_tiles = static_cast<int>((e.Ma + hs.BM - 1) / hs.BM);
     t.n_slices = slices;
-    const int col_tiles = static_cast<int>((e.Nb + BN - 1) / BN);
+    const int col_tiles = static_cast<int>((e.Nb + hs.BN - 1) / hs.BN);
     t.tiles_per_slice = (col_tiles + slices - 1) / slices;
     t.mask_rowptr = e.mask_rowptr; t.mask_col = e.mask_col;
     t.exclude_self = e.exclude_self; t.self_off = e.self_off;
@@ -864,7 +885,7 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     }
 
     RescoreArgs r{};
-    r.A = e.A; r.B = e.B; r.Ma = e.Ma; r.Nb = e.Nb; r.D = e.d; r.K = e.K; r.n_slices = slices * kColHalves; r.kp = kp;
+    r.A = e.A; r.B = e.B; r.Ma = e.Ma; r.Nb = e.Nb; r.D = e.d; r.K = e.K; r.n_slices = slices * hs.CH; r.kp = kp;
     r.cand = cand_out; r.tprime = tprime; r.a_norm = a_norm; r.b_norm_max = b_max;
     // |bf16(x)-x| <= 2^-9|x| per operand -> products within (2^-8 + 2^-18) relative; tensor-core fp32
     // accumulation (assumed no worse than truncation per add) and the canonical chain's own rounding
