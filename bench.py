@@ -82,7 +82,13 @@ def make_eval_job(cfg, scale):
     return dict(U=U, I=I, d=d, K=cfg["K"], user=u, item=it, mask_rowptr=mask_rowptr, mask_col=mi.to(torch.int32), pos=pos)
 
 
-def shard_eval_job(job, lo, hi):
+def shard_eval_job(job, lo, hi, n_chunks=1):
+    """Pinned host buffers of users [lo, hi); with n_chunks > 1 a list of consecutive chunks (for the
+    copy/compute-overlapped end-to-end path)."""
+    if n_chunks > 1:
+        n = hi - lo
+        bounds = [lo + (n * i) // n_chunks for i in range(n_chunks + 1)]
+        return [shard_eval_job(job, bounds[i], bounds[i + 1]) for i in range(n_chunks) if bounds[i + 1] > bounds[i]]
     from chaorec_b200.ranking import HostEvalBatch
     rp = job["mask_rowptr"]
     m_lo, m_hi = int(rp[lo]), int(rp[hi])
@@ -183,6 +189,7 @@ def run_eval_leg(args, dev, rank, world, peaks):
     U, I, d, K = job["U"], job["I"], job["d"], job["K"]
     lo, hi = cdist.shard_range(U, world, rank)
     batch = shard_eval_job(job, lo, hi)
+    e2e_chunks = shard_eval_job(job, lo, hi, n_chunks=max(1, min(4, (hi - lo) // 200_000)))
     n_local = hi - lo
     ks = [5, 10, 20]
 
@@ -230,13 +237,18 @@ def run_eval_leg(args, dev, rank, world, peaks):
     value = U * args.steps / t_total
 
     # ---- end-to-end leg (host buffers in, metrics out) ------------------------------------------
+    n_pos_all = np.full(U, job["pos"].shape[1], dtype=np.int32)
+
     def e2e_step():
-        h = evaluate_host_batch(batch, K, dev)
-        all_h = cdist.gather_to_rank0(h)
-        if rank == 0:
+        h = evaluate_host_batch(e2e_chunks, K, dev)          # pinned host tensor, synchronised
+        if world > 1:
+            all_h = cdist.gather_to_rank0(h.to(dev))
+            if rank != 0:
+                return None
             hh = all_h.cpu().numpy()
-            return metrics_from_hits(hh, np.full(U, job["pos"].shape[1], dtype=np.int32), ks)
-        return None
+        else:
+            hh = h.numpy()
+        return metrics_from_hits(hh, n_pos_all, ks)
 
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()

@@ -245,19 +245,43 @@ class HostEvalBatch:
                                                           self.mask_col, self.pos_rowptr, self.pos_col))
 
 
-def evaluate_host_batch(batch: HostEvalBatch, topk: int, device: torch.device, mask_value: float = 1e-6):
+def evaluate_host_batch(batch, topk: int, device: torch.device, mask_value: float = 1e-6):
     """Host buffers in, hit masks out: H2D copies, fused ranking, hit masks, D2H -- the part of an
-    end-to-end evaluation that runs per rank.  Returns (hits int64 numpy [U_local], d2h bytes)."""
-    ue = batch.user_emb.to(device, non_blocking=True)
-    ie = batch.item_emb.to(device, non_blocking=True)
-    mask = MaskCSR(batch.mask_rowptr.to(device, non_blocking=True), batch.mask_col.to(device, non_blocking=True))
-    pos = PositivesCSR(None, batch.pos_rowptr.to(device, non_blocking=True), batch.pos_col.to(device, non_blocking=True),
-                       batch.n_pos)
-    ranks = rank_topk(ue, ie, mask, topk, mask_value, batch.id_offset)
+    end-to-end evaluation that runs per rank.  ``batch`` is one ``HostEvalBatch`` or a list of them
+    (consecutive user chunks sharing one item table): with a list, the copies of chunk i+1 run on a
+    second stream while chunk i is ranked, and the hit masks stream back as they are produced.
+    Returns the hit masks as a pinned int64 host tensor [U_local] (synchronised)."""
+    chunks = batch if isinstance(batch, (list, tuple)) else [batch]
     lib = _lib.load()
-    hits = torch.empty(ue.shape[0], dtype=torch.int64, device=device)
-    with torch.cuda.device(device):
-        rc = lib.chaorec_topk_hits(_lib.ptr(ranks), None, _lib.ptr(pos.rowptr), _lib.ptr(pos.col), ue.shape[0], int(topk),
-                                   _lib.ptr(hits), _lib.stream_ptr(device))
-    _lib.check(rc, "chaorec_topk_hits")
-    return hits
+    cur = torch.cuda.current_stream(device)
+    copy_stream = torch.cuda.Stream(device=device)
+    total = sum(c.user_emb.shape[0] for c in chunks)
+    hits_host = torch.empty(total, dtype=torch.int64, pin_memory=True)
+    keep = []
+    staged = []
+    with torch.cuda.stream(copy_stream):
+        ie = chunks[0].item_emb.to(device, non_blocking=True)
+        for c in chunks:
+            dev_t = (c.user_emb.to(device, non_blocking=True), c.mask_rowptr.to(device, non_blocking=True),
+                     c.mask_col.to(device, non_blocking=True), c.pos_rowptr.to(device, non_blocking=True),
+                     c.pos_col.to(device, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            staged.append((dev_t, ev))
+    off = 0
+    for c, (dev_t, ev) in zip(chunks, staged):
+        cur.wait_event(ev)
+        ue, m_rp, m_col, p_rp, p_col = dev_t
+        ranks = rank_topk(ue, ie, MaskCSR(m_rp, m_col), topk, mask_value, c.id_offset)
+        n = ue.shape[0]
+        hits = torch.empty(n, dtype=torch.int64, device=device)
+        with torch.cuda.device(device):
+            rc = lib.chaorec_topk_hits(_lib.ptr(ranks), None, _lib.ptr(p_rp), _lib.ptr(p_col), n, int(topk),
+                                       _lib.ptr(hits), _lib.stream_ptr(device))
+        _lib.check(rc, "chaorec_topk_hits")
+        hits_host[off:off + n].copy_(hits, non_blocking=True)
+        keep.append((ranks, hits))
+        off += n
+    cur.synchronize()
+    copy_stream.synchronize()
+    return hits_host

@@ -238,3 +238,25 @@ def test_tensor_engine_is_used_and_rarely_falls_back(canon, engine):
     hrp, hcol = _csr_np(heavy)
     cidx, _ = canon.score_mask_topk(u.numpy(), it.numpy(), hrp, hcol, 1e-6, K, 0)
     assert np.array_equal(idx.cpu().numpy(), cidx)
+
+
+def test_host_batch_path_chunked_equals_single():
+    """The end-to-end host-buffer API (pinned host -> device copies overlapped with ranking)."""
+    import bench
+    from chaorec_b200.ranking import evaluate_host_batch, metrics_from_hits
+    job = bench.make_eval_job(dict(bench.EVAL_CFG, U=6000, I=3000), 1.0)
+    single = bench.shard_eval_job(job, 0, job["U"])
+    chunks = bench.shard_eval_job(job, 0, job["U"], n_chunks=3)
+    assert isinstance(chunks, list) and len(chunks) == 3
+    h1 = evaluate_host_batch(single, job["K"], dev()).numpy().copy()
+    h3 = evaluate_host_batch(chunks, job["K"], dev()).numpy().copy()
+    assert np.array_equal(h1, h3)
+    # the same job through rank_topk + evaluate
+    mask = cb.MaskCSR(job["mask_rowptr"].to(dev()), job["mask_col"].to(dev()))
+    rank = cb.rank_topk(job["user"].to(dev()), job["item"].to(dev()), mask, job["K"], 1e-6, job["U"])
+    rows = np.empty(job["U"], dtype=object)
+    for u, p in enumerate(job["pos"].tolist()):
+        rows[u] = [u] + p
+    want = cb.evaluate(None, rows, rank, [5, 10, 20])
+    got = metrics_from_hits(h3, np.full(job["U"], job["pos"].shape[1], dtype=np.int32), [5, 10, 20])
+    assert got == want
