@@ -86,9 +86,11 @@ def shard_eval_job(job, lo, hi, n_chunks=1):
     """Pinned host buffers of users [lo, hi); with n_chunks > 1 a list of consecutive chunks (for the
     copy/compute-overlapped end-to-end path)."""
     if n_chunks > 1:
+        # a small first chunk (its copies are exposed), the rest in one piece (its copies hide behind
+        # the first chunk's kernels)
         n = hi - lo
-        bounds = [lo + (n * i) // n_chunks for i in range(n_chunks + 1)]
-        return [shard_eval_job(job, bounds[i], bounds[i + 1]) for i in range(n_chunks) if bounds[i + 1] > bounds[i]]
+        bounds = [lo, lo + n // 5, hi]
+        return [shard_eval_job(job, bounds[i], bounds[i + 1]) for i in range(2) if bounds[i + 1] > bounds[i]]
     from chaorec_b200.ranking import HostEvalBatch
     rp = job["mask_rowptr"]
     m_lo, m_hi = int(rp[lo]), int(rp[hi])
@@ -189,7 +191,7 @@ def run_eval_leg(args, dev, rank, world, peaks):
     U, I, d, K = job["U"], job["I"], job["d"], job["K"]
     lo, hi = cdist.shard_range(U, world, rank)
     batch = shard_eval_job(job, lo, hi)
-    e2e_chunks = shard_eval_job(job, lo, hi, n_chunks=max(1, min(4, (hi - lo) // 200_000)))
+    e2e_chunks = shard_eval_job(job, lo, hi, n_chunks=2 if (hi - lo) >= 400_000 else 1)
     n_local = hi - lo
     ks = [5, 10, 20]
 

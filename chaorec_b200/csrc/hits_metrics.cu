@@ -57,33 +57,43 @@ extern "C" int chaorec_metrics_from_hits(const uint64_t *hit_mask, const int32_t
     for (int t = 0; t < n_k; ++t)
         if (ks[t] < 1 || ks[t] > 64) return CHAOREC_E_UNSUPPORTED;
     for (int t = 0; t < n_k * 5; ++t) out[t] = 0.0;
+    // idcg(lim) = sum([inv_log[i] for i in range(lim)]) accumulated left to right (metrics.py:31):
+    // the sequential prefix sums are exactly those partial sums
+    double idcg_prefix[65];
+    idcg_prefix[0] = 0.0;
+    int max_k = 0;
+    for (int t = 0; t < n_k; ++t) max_k = ks[t] > max_k ? ks[t] : max_k;
+    for (int i = 0; i < max_k; ++i) idcg_prefix[i + 1] = idcg_prefix[i] + inv_log[i];
+    const uint64_t any_mask = (max_k == 64) ? ~0ull : ((1ull << max_k) - 1ull);
     for (int64_t row = 0; row < n_rows; ++row) {
         const uint64_t mask = hit_mask[row];
+        // A row without a hit inside max(k) adds +0 to every running sum (0/k, 0/len, 0/idcg, 0, 0/len):
+        // x + 0.0 == x exactly, so skipping it leaves every sum bit-identical.
+        if ((mask & any_mask) == 0ull) continue;
         const int np = n_pos_of_row[row];
         for (int t = 0; t < n_k; ++t) {
             const int k = ks[t];
-            const uint64_t m = (k == 64) ? mask : (mask & ((1ull << k) - 1ull));
+            uint64_t m = (k == 64) ? mask : (mask & ((1ull << k) - 1ull));
+            if (m == 0ull) continue;
             const int inter = __builtin_popcountll(m);
             double *o = out + t * 5;
             o[0] += static_cast<double>(inter) / static_cast<double>(k);              // metrics.py:16
             if (np > 0) o[1] += static_cast<double>(inter) / static_cast<double>(np);  // metrics.py:20-23
             if (np > 0) {                                                              // metrics.py:28-39
-                double idcg = 0.0;
-                const int lim = np < k ? np : k;
-                for (int i = 0; i < lim; ++i) idcg += inv_log[i];
+                const double idcg = idcg_prefix[np < k ? np : k];
                 double dcg = 0.0, ap = 0.0;
                 int n_hit = 0;
-                for (int i = 0; i < k; ++i) {
-                    if ((m >> i) & 1ull) {
-                        dcg += inv_log[i];
-                        ++n_hit;
-                        ap += static_cast<double>(n_hit) / static_cast<double>(i + 1);  // metrics.py:53-56
-                    }
+                while (m) {                                                            // hits in rank order
+                    const int i = __builtin_ctzll(m);
+                    m &= m - 1ull;
+                    dcg += inv_log[i];
+                    ++n_hit;
+                    ap += static_cast<double>(n_hit) / static_cast<double>(i + 1);     // metrics.py:53-56
                 }
                 o[2] += dcg / idcg;
-                o[4] += ap / static_cast<double>(np);                                   // metrics.py:57
+                o[4] += ap / static_cast<double>(np);                                  // metrics.py:57
             }
-            o[3] += inter > 0 ? 1.0 : 0.0;                                              // metrics.py:44
+            o[3] += 1.0;                                                               // metrics.py:44
         }
     }
     if (n_rows > 0)

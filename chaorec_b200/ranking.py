@@ -245,6 +245,9 @@ class HostEvalBatch:
                                                           self.mask_col, self.pos_rowptr, self.pos_col))
 
 
+_host_path_cache: Dict[Tuple[int, int], Tuple[torch.cuda.Stream, torch.Tensor]] = {}
+
+
 def evaluate_host_batch(batch, topk: int, device: torch.device, mask_value: float = 1e-6):
     """Host buffers in, hit masks out: H2D copies, fused ranking, hit masks, D2H -- the part of an
     end-to-end evaluation that runs per rank.  ``batch`` is one ``HostEvalBatch`` or a list of them
@@ -254,9 +257,15 @@ def evaluate_host_batch(batch, topk: int, device: torch.device, mask_value: floa
     chunks = batch if isinstance(batch, (list, tuple)) else [batch]
     lib = _lib.load()
     cur = torch.cuda.current_stream(device)
-    copy_stream = torch.cuda.Stream(device=device)
     total = sum(c.user_emb.shape[0] for c in chunks)
-    hits_host = torch.empty(total, dtype=torch.int64, pin_memory=True)
+    key = (device.index, total)
+    cached = _host_path_cache.get(key)
+    if cached is None:     # pinned allocations and stream creation are slow: once per shape
+        cached = (torch.cuda.Stream(device=device), torch.empty(total, dtype=torch.int64, pin_memory=True))
+        _host_path_cache.clear()
+        _host_path_cache[key] = cached
+    copy_stream, hits_host = cached
+    copy_stream.wait_stream(cur)
     keep = []
     staged = []
     with torch.cuda.stream(copy_stream):

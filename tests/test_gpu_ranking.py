@@ -247,7 +247,7 @@ def test_host_batch_path_chunked_equals_single():
     job = bench.make_eval_job(dict(bench.EVAL_CFG, U=6000, I=3000), 1.0)
     single = bench.shard_eval_job(job, 0, job["U"])
     chunks = bench.shard_eval_job(job, 0, job["U"], n_chunks=3)
-    assert isinstance(chunks, list) and len(chunks) == 3
+    assert isinstance(chunks, list) and len(chunks) == 2
     h1 = evaluate_host_batch(single, job["K"], dev()).numpy().copy()
     h3 = evaluate_host_batch(chunks, job["K"], dev()).numpy().copy()
     assert np.array_equal(h1, h3)
