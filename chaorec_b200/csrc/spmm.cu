@@ -298,6 +298,100 @@ __global__ void __launch_bounds__(kThreads) spmm_rows_seg_kernel(const SpmmArgs 
     }
 }
 
+// ---- hot-column staging -----------------------------------------------------------------------
+// Both the sub-warp kernel and the hub kernels top out near 6 TB/s of L2->SM traffic whether the
+// gathers hit in L2 or go to HBM (profiles/: rows kernel 45 GB in 8.5 ms, hub chunks 17 GB from
+// DRAM in 2.75 ms), so the lever left is to take traffic OFF the L2->SM path.  Item popularity is
+// Zipf-like: at the 100M-edge config the 768 most frequent columns receive 48 % of all user->item
+// edges.  A persistent CTA stages the x rows of those columns (768 x 256 B = 192 KB) in shared
+// memory once per launch; the CSR carries a second column array in which hot columns are encoded
+// as -1-slot, so the inner loop picks shared or global memory with one sign test.
+struct HotArgs {
+    const int32_t *col_enc;    // [nnz] column index, or -1-slot for a staged column
+    const int32_t *hot_cols;   // [n_hot] slot -> column
+    int n_hot;
+};
+
+template <int LANES, int NV>
+__global__ void __launch_bounds__(1024, 1) spmm_rows_hot_kernel(const SpmmArgs a, const HotArgs h) {
+    extern __shared__ __align__(16) unsigned char hot_smem[];
+    float4 *hot_x = reinterpret_cast<float4 *>(hot_smem);                      // [n_hot][dq]
+    float *hot_cs = reinterpret_cast<float *>(hot_x + static_cast<size_t>(h.n_hot) * a.dq);   // [n_hot]
+    constexpr int kGroups = 1024 / LANES;
+    const int lane = threadIdx.x & 31;
+    const int gl = threadIdx.x % LANES;
+    const int g = threadIdx.x / LANES;
+    const unsigned mask = group_mask<LANES>(lane);
+    for (int sl = g; sl < h.n_hot; sl += kGroups) {
+        const int64_t c = __ldg(h.hot_cols + sl);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int q = gl + v * LANES;
+            if (q < a.dq) hot_x[static_cast<size_t>(sl) * a.dq + q] = __ldg(a.x + c * a.dq + q);
+        }
+        if (gl == 0) hot_cs[sl] = a.col_scale ? __ldg(a.col_scale + c) : 1.0f;
+    }
+    __syncthreads();
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * kGroups + g; r < a.M; r += static_cast<int64_t>(gridDim.x) * kGroups) {
+        const int64_t e_lo = __ldg(a.rowptr + r), e_hi = __ldg(a.rowptr + r + 1);
+        if (a.hub_rows != nullptr && e_hi - e_lo > kHubThreshold) continue;   // taken by the hub kernels
+        float4 acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t e0 = e_lo; e0 < e_hi; e0 += LANES) {
+            const int64_t e = e0 + gl;
+            int c = 0;
+            float w = 0.0f;
+            if (e < e_hi) {
+                c = __ldg(h.col_enc + e);
+                w = a.val ? __ldg(a.val + e) : 1.0f;
+                if (c < 0) w *= hot_cs[-1 - c];
+                else if (a.col_scale) w *= __ldg(a.col_scale + c);
+            }
+            const int cnt = (e_hi - e0 < LANES) ? static_cast<int>(e_hi - e0) : LANES;
+            for (int j = 0; j < cnt; j += 4) {
+                const int nb = (cnt - j < 4) ? (cnt - j) : 4;
+                int cj[4];
+                float wj[4];
+                float4 xv[4][NV];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    cj[t] = __shfl_sync(mask, c, (j + t) % LANES, LANES);
+                    wj[t] = __shfl_sync(mask, w, (j + t) % LANES, LANES);
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (t < nb) {
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            const int q = gl + v * LANES;
+                            if (q < a.dq) {
+                                xv[t][v] = (cj[t] < 0) ? hot_x[static_cast<size_t>(-1 - cj[t]) * a.dq + q]
+                                                       : __ldg(a.x + static_cast<int64_t>(cj[t]) * a.dq + q);
+                            } else {
+                                xv[t][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (t < nb) {
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            acc[v].x = fmaf(wj[t], xv[t][v].x, acc[v].x);
+                            acc[v].y = fmaf(wj[t], xv[t][v].y, acc[v].y);
+                            acc[v].z = fmaf(wj[t], xv[t][v].z, acc[v].z);
+                            acc[v].w = fmaf(wj[t], xv[t][v].w, acc[v].w);
+                        }
+                    }
+                }
+            }
+        }
+        row_epilogue<LANES, NV>(a, r, gl, acc);
+    }
+}
+
 // One CTA per (hub row, chunk): every sub-warp reduces a contiguous slice of the chunk, the
 // slices are summed in slice order through shared memory and stored as one partial row.
 template <int LANES, int NV>
@@ -367,11 +461,20 @@ __global__ void __launch_bounds__(kThreads) spmm_hub_finish_kernel(const SpmmArg
 }
 
 template <int LANES, int NV>
-int launch_spmm(const SpmmArgs &a, int64_t n_hub_chunks, cudaStream_t st) {
+int launch_spmm(const SpmmArgs &a, const HotArgs &h, int64_t n_hub_chunks, cudaStream_t st) {
     constexpr int kGroups = kThreads / LANES;
     const int64_t blocks = (a.M + kGroups - 1) / kGroups;
     if (blocks > 0x7fffffffLL) return CHAOREC_E_UNSUPPORTED;
-    if constexpr (LANES > kRowsPerGroup) {
+    if (h.col_enc != nullptr && h.n_hot > 0 && a.M > 0) {
+        const size_t smem = static_cast<size_t>(h.n_hot) * a.dq * 16 + static_cast<size_t>(h.n_hot) * 4 + 16;
+        if (cudaFuncSetAttribute(spmm_rows_hot_kernel<LANES, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)) != cudaSuccess) {
+            cudaGetLastError();
+            return CHAOREC_E_LAUNCH;
+        }
+        spmm_rows_hot_kernel<LANES, NV><<<sm_count(), 1024, smem, st>>>(a, h);
+    } else
+    if constexpr (LANES > kRowsPerGroup && false) {   // measured slower (80 regs, 10.1 ms vs 8.5 ms at the 100M-edge config)
         const int64_t seg_blocks = (a.M + static_cast<int64_t>(kGroups) * kRowsPerGroup - 1) / (static_cast<int64_t>(kGroups) * kRowsPerGroup);
         if (seg_blocks > 0) spmm_rows_seg_kernel<LANES, NV><<<static_cast<unsigned>(seg_blocks), kThreads, 0, st>>>(a);
     } else {
@@ -413,11 +516,12 @@ extern "C" int chaorec_degree_inv_sqrt(const int64_t *rowptr, int64_t M, float e
     return launch_status();
 }
 
-extern "C" int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float *val,
-                                    const float *row_scale, const float *col_scale, const float *x, float *y,
-                                    float *acc, float alpha, int32_t acc_mode, const int32_t *hub_rows,
-                                    const int64_t *hub_chunk_ptr, int32_t n_hub, int64_t n_hub_chunks,
-                                    float *hub_partials, int64_t M, int64_t N, int32_t d, void *stream) {
+extern "C" int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *col, const float *val,
+                                        const float *row_scale, const float *col_scale, const float *x, float *y,
+                                        float *acc, float alpha, int32_t acc_mode, const int32_t *hub_rows,
+                                        const int64_t *hub_chunk_ptr, int32_t n_hub, int64_t n_hub_chunks,
+                                        float *hub_partials, const int32_t *hot_col_enc, const int32_t *hot_cols,
+                                        int32_t n_hot, int64_t M, int64_t N, int32_t d, void *stream) {
     if (!rowptr || !x || M < 0 || N < 0 || d <= 0) return CHAOREC_E_BADARG;
     if (!y && !acc) return CHAOREC_E_BADARG;
     if (acc_mode != 0 && acc_mode != 1) return CHAOREC_E_BADARG;
@@ -439,10 +543,25 @@ extern "C" int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, c
     a.hub_partials = reinterpret_cast<float4 *>(hub_partials);
     a.M = M; a.dq = d / 4;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (d == 32) return launch_spmm<8, 1>(a, n_hub_chunks, st);
-    if (d == 64) return launch_spmm<16, 1>(a, n_hub_chunks, st);
-    if (d <= 128) return launch_spmm<32, 1>(a, n_hub_chunks, st);
-    if (d <= 256) return launch_spmm<32, 2>(a, n_hub_chunks, st);
-    if (d <= 384) return launch_spmm<32, 3>(a, n_hub_chunks, st);
-    return launch_spmm<32, 4>(a, n_hub_chunks, st);
+    HotArgs h{};
+    h.col_enc = hot_col_enc; h.hot_cols = hot_cols; h.n_hot = (hot_col_enc && hot_cols) ? n_hot : 0;
+    if (h.n_hot > 0 && static_cast<size_t>(h.n_hot) * d * 4 + static_cast<size_t>(h.n_hot) * 4 + 16 > 220 * 1024)
+        return CHAOREC_E_UNSUPPORTED;
+    if (h.n_hot == 0) h.col_enc = nullptr;
+    if (d == 32) return launch_spmm<8, 1>(a, h, n_hub_chunks, st);
+    if (d == 64) return launch_spmm<16, 1>(a, h, n_hub_chunks, st);
+    if (d <= 128) return launch_spmm<32, 1>(a, h, n_hub_chunks, st);
+    if (d <= 256) return launch_spmm<32, 2>(a, h, n_hub_chunks, st);
+    if (d <= 384) return launch_spmm<32, 3>(a, h, n_hub_chunks, st);
+    return launch_spmm<32, 4>(a, h, n_hub_chunks, st);
+}
+
+extern "C" int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float *val,
+                                    const float *row_scale, const float *col_scale, const float *x, float *y,
+                                    float *acc, float alpha, int32_t acc_mode, const int32_t *hub_rows,
+                                    const int64_t *hub_chunk_ptr, int32_t n_hub, int64_t n_hub_chunks,
+                                    float *hub_partials, int64_t M, int64_t N, int32_t d, void *stream) {
+    return chaorec_spmm_csr_hot_f32(rowptr, col, val, row_scale, col_scale, x, y, acc, alpha, acc_mode, hub_rows,
+                                    hub_chunk_ptr, n_hub, n_hub_chunks, hub_partials, nullptr, nullptr, 0, M, N, d,
+                                    stream);
 }

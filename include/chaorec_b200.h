@@ -89,6 +89,20 @@ int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float 
                          int32_t n_hub, int64_t n_hub_chunks, float *hub_partials, int64_t M, int64_t N,
                          int32_t d, void *stream);
 
+/*
+ * Same product with hot-column staging: hot_col_enc int32 [nnz] is `col` with the n_hot most
+ * frequent columns replaced by -1-slot, hot_cols int32 [n_hot] maps slot -> column.  The x rows of
+ * those columns are staged in shared memory once per launch by persistent CTAs (item popularity
+ * is Zipf-like: a few hundred columns receive about half of the user->item gathers), which takes
+ * that traffic off the L2->SM path.  n_hot * (4d + 4) must fit in 220 KB.  hot_col_enc == NULL
+ * is exactly chaorec_spmm_csr_f32.
+ */
+int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *col, const float *val, const float *row_scale,
+                             const float *col_scale, const float *x, float *y, float *acc, float alpha,
+                             int32_t acc_mode, const int32_t *hub_rows, const int64_t *hub_chunk_ptr,
+                             int32_t n_hub, int64_t n_hub_chunks, float *hub_partials, const int32_t *hot_col_enc,
+                             const int32_t *hot_cols, int32_t n_hot, int64_t M, int64_t N, int32_t d, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * (2) Full-ranking evaluation
  * ---------------------------------------------------------------------------------------- */
