@@ -58,8 +58,8 @@ __device__ __forceinline__ void gather_edges(const SpmmArgs &a, int64_t e_lo, in
         int c = 0;
         float w = 0.0f;
         if (e < e_hi) {
-            c = __ldg(a.col + e);
-            w = a.val ? __ldg(a.val + e) : 1.0f;
+            c = __ldcs(a.col + e);                       // streamed once: do not displace gathered rows in L2
+            w = a.val ? __ldcs(a.val + e) : 1.0f;
             if (a.col_scale) w *= __ldg(a.col_scale + c);
         }
         const int cnt = (e_hi - e0 < LANES) ? static_cast<int>(e_hi - e0) : LANES;
@@ -155,20 +155,20 @@ __device__ __forceinline__ void row_epilogue(const SpmmArgs &a, int64_t r, int g
             yv.x *= rs; yv.y *= rs; yv.z *= rs; yv.w *= rs;
         }
         const int64_t o = r * a.dq + q;
-        if (a.y) a.y[o] = yv;
+        if (a.y) a.y[o] = yv;                            // next layer gathers these rows: normal policy
         if (a.acc) {
             float4 base;
             if (a.acc_mode == 1) {
                 const float4 x0 = __ldg(a.x + o);
                 base = make_float4(a.alpha * x0.x, a.alpha * x0.y, a.alpha * x0.z, a.alpha * x0.w);
             } else {
-                base = a.acc[o];
+                base = __ldcs(a.acc + o);                // running layer mean: streamed
             }
             base.x = fmaf(a.alpha, yv.x, base.x);
             base.y = fmaf(a.alpha, yv.y, base.y);
             base.z = fmaf(a.alpha, yv.z, base.z);
             base.w = fmaf(a.alpha, yv.w, base.w);
-            a.acc[o] = base;
+            __stcs(a.acc + o, base);
         }
     }
 }

@@ -9,6 +9,7 @@ Host logic only; all arithmetic runs in csrc/spmm.cu through the C ABI.
 """
 from __future__ import annotations
 
+import os
 import weakref
 from dataclasses import dataclass, field
 from typing import Dict, Optional, Tuple
@@ -78,6 +79,12 @@ class CSRGraph:
         if d in self._hot:
             return self._hot[d]
         plan = None
+        if os.environ.get("CHAOREC_SPMM_HOT", "0") != "1":
+            # Measured at the 100M-edge config (profiles/README.md): staging the 768 most frequent columns
+            # in shared memory leaves the kernel time unchanged (8.5 ms) -- those rows were L2 hits already
+            # and the kernel is bound by the random HBM gathers of the cold rows.  Kept behind a switch.
+            self._hot[d] = None
+            return None
         n_hot = min(((200 * 1024) // (4 * d + 4)) // 64 * 64, self.N)
         if self.nnz >= (1 << 22) and n_hot >= 64:
             counts = torch.bincount(self.col.to(torch.int64), minlength=self.N)
