@@ -225,32 +225,97 @@ __device__ __forceinline__ void mask_padding(uint32_t (&v)[32], uint32_t col0, u
 
 constexpr int kKeysPerLane = TC_CAP / 32;
 
-// Mid-run compaction of one row's list (n entries in global memory), executed by a whole warp:
-// a 32-step bitwise search finds the (r+1)-th largest score (keys are spread 16 per lane in
-// registers, counts are combined with redux.sync), entries below it are dropped, the survivors
-// are written back in arbitrary order.  No sort, no validity lookups: r already includes one
-// slot for every column that may later turn out to be invalid (train items, the row itself).
-// Returns the new count and the new threshold (ties at the threshold are kept, so the count can
-// exceed r+1; the caller treats a list that is still too long as uncertifiable).
-__device__ __forceinline__ void tc_select(uint64_t *row_buf, int n, int r, int lane, int &new_cnt, float &new_tau) {
+// In a 256-bin histogram (shared memory, bins in DESCENDING order of value) find the bin in which
+// the running count from the top reaches `rank1` (1-based) and the count strictly above that bin.
+__device__ __forceinline__ void hist_find(const uint32_t *hist, int lane, int rank1, int &bin, int &above) {
+    uint32_t my[8];
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {          // lane l owns bins 255-8l .. 248-8l
+        my[j] = hist[255 - 8 * lane - j];
+        sum += static_cast<int>(my[j]);
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int excl = incl - sum;
+    const bool has = excl < rank1 && rank1 <= incl;
+    int b = 0, ab = 0;
+    if (has) {
+        int cum = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (b == 0 && cum + static_cast<int>(my[j]) >= rank1) { b = 256 - 8 * lane - j; ab = cum; }   // b stored +1
+            cum += static_cast<int>(my[j]);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    const int src = m ? (__ffs(m) - 1) : 0;
+    bin = __shfl_sync(0xffffffffu, b, src) - 1;
+    above = __shfl_sync(0xffffffffu, ab, src);
+    if (m == 0u) { bin = 0; above = 0; }
+}
+
+// Mid-run compaction of one row's list (n raw entries in global memory, n > r), executed by a whole
+// warp.  Keys sit 8 per lane in registers; the (r+1)-th largest score is located by two 256-bin
+// histogram passes over the 16 bits below the highest bit in which the list's scores differ
+// (shared-memory atomics + one warp scan per pass) instead of a bit-by-bit search; entries below the
+// resulting threshold are dropped, the survivors are written back in arbitrary order.  The threshold
+// is a lower bound of the exact (r+1)-th score (anything below the resolved 16 bits rounds down), so
+// a few extra entries may survive -- never too few.  No sort, no validity lookups: r already includes
+// one slot for every column that may later turn out to be invalid (train items, the row itself).
+__device__ __forceinline__ void tc_select(uint64_t *row_buf, int n, int r, int lane, uint32_t *hist, int &new_cnt,
+                                          float &new_tau) {
     uint64_t k[kKeysPerLane];
+    uint32_t lo = 0xFFFFFFFFu, mx = 0u;
 #pragma unroll
     for (int i = 0; i < kKeysPerLane; ++i) {
         const int idx = lane + 32 * i;
         k[i] = (idx < n) ? key_of_raw(row_buf[idx]) : 0ull;
+        if (k[i] != 0ull) {
+            const uint32_t hi = static_cast<uint32_t>(k[i] >> 32);
+            lo = min(lo, hi);
+            mx = max(mx, hi);
+        }
     }
-    // 18 of the 32 score bits are resolved: the threshold is then at most 2^-9 (relative) below the
-    // exact (r+1)-th score -- any lower bound is valid, it only keeps a few more entries -- and the
-    // search costs half as much (approximate scores carry 8 significant bits anyway)
-    uint32_t prefix = 0;
-#pragma unroll 1
-    for (int b = 31; b >= 14; --b) {
-        const uint32_t cand = prefix | (1u << b);
-        int c = 0;
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    uint32_t prefix = mx;
+    if (lo != mx) {
+        const int p = 31 - __clz(lo ^ mx);                 // highest differing bit
+        const int s1 = p >= 7 ? p - 7 : 0;
+        const uint32_t common = (s1 + 8 >= 32) ? 0u : ((mx >> (s1 + 8)) << (s1 + 8));
 #pragma unroll
-        for (int i = 0; i < kKeysPerLane; ++i) c += (static_cast<uint32_t>(k[i] >> 32) >= cand) ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c >= r + 1) prefix = cand;
+        for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0u;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < kKeysPerLane; ++i)
+            if (k[i] != 0ull) atomicAdd(&hist[(static_cast<uint32_t>(k[i] >> 32) >> s1) & 255u], 1u);
+        __syncwarp();
+        int bin1, above1;
+        hist_find(hist, lane, r + 1, bin1, above1);
+        prefix = common | (static_cast<uint32_t>(bin1) << s1);
+        if (s1 > 0) {
+            const int s2 = s1 >= 8 ? s1 - 8 : 0;
+            const uint32_t sel = (common >> s1) | static_cast<uint32_t>(bin1);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0u;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < kKeysPerLane; ++i) {
+                const uint32_t hi = static_cast<uint32_t>(k[i] >> 32);
+                if (k[i] != 0ull && (hi >> s1) == sel) atomicAdd(&hist[(hi >> s2) & ((1u << (s1 - s2)) - 1u)], 1u);
+            }
+            __syncwarp();
+            int bin2, above2;
+            hist_find(hist, lane, r + 1 - above1, bin2, above2);
+            prefix |= static_cast<uint32_t>(bin2) << s2;
+        }
+        __syncwarp();
     }
     int mine = 0;
 #pragma unroll
@@ -525,7 +590,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     uint64_t *buf_src = a.cand_ws + (list0 + static_cast<size_t>(src) * CH) * TC_CAP;
                     int nc;
                     float nt;
-                    tc_select(buf_src, n_src < TC_CAP ? n_src : TC_CAP, r_src, lane, nc, nt);
+                    tc_select(buf_src, n_src < TC_CAP ? n_src : TC_CAP, r_src, lane, reinterpret_cast<uint32_t *>(scratch), nc, nt);
                     if (lane == src) {
                         if (n_src > TC_CAP || nc > kTcTrigger) {  // (cannot overflow) / a huge run of exact ties
                             give_up = true;
@@ -556,7 +621,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     uint64_t *buf_src = a.cand_ws + (list0 + static_cast<size_t>(src) * CH) * TC_CAP;
                     if (n_src > r_src + 1) {                      // cut to the r_keep best before sorting
                         float nt;
-                        tc_select(buf_src, n_src, r_src, lane, n_src, nt);
+                        tc_select(buf_src, n_src, r_src, lane, reinterpret_cast<uint32_t *>(scratch), n_src, nt);
                         tau_src = nt;
                     }
                     if (n_src <= kTcTrigger) {
@@ -792,10 +857,17 @@ int tc_choose_slices(int64_t Ma, int64_t Nb, int D) {
     const int row_tiles = static_cast<int>((Ma + hs.BM - 1) / hs.BM);
     const int col_tiles = static_cast<int>((Nb + hs.BN - 1) / hs.BN);
     const int sms = sm_count();
+    // Column slices trade load balance for repeated list warm-up (every slice restarts its rows'
+    // thresholds at -inf): estimated time ~ rounds(units / SMs) * (1/slices + restart), restart ~ 8 %
+    // of an unsliced unit.  At most 4 slices so that n_lists * K' + K candidates fit the re-score buffer.
     int slices = 1;
-    // enough units to balance the persistent grid (>= 4 waves of work items), at most 4 slices so
-    // that n_lists * K' + K candidates fit the re-score buffer
-    while (slices < 4 && row_tiles * slices < 4 * sms && col_tiles / (slices * 2) >= 8) slices *= 2;
+    double best = 1e30;
+    for (int s = 1; s <= 4; s *= 2) {
+        if (s > 1 && col_tiles / s < 16) break;
+        const int rounds = (row_tiles * s + sms - 1) / sms;
+        const double cost = rounds * (1.0 / s + 0.08);
+        if (cost < best - 1e-9) { best = cost; slices = s; }
+    }
     return slices;
 }
 
