@@ -566,19 +566,21 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     continue;
                 }
                 tmem_ld32(taddr + ch * 64, va);
-                tmem_ld_wait();
-                __syncwarp();
                 tmem_ld32(taddr + ch * 64 + 32, vb);
-                if (last_tile) mask_padding(va, tcol, nb32);
-                wr = filter_chunk(va, tau, tcol, wr);
                 tmem_ld_wait();
-                if (last_tile) mask_padding(vb, tcol + 32, nb32);
-                wr = filter_chunk(vb, tau, tcol + 32, wr);
-                cnt = static_cast<int>(wr - row_buf);
+                // the 64 scores of this thread are in registers: hand the accumulator stage back to the
+                // MMA warp BEFORE filtering, so that the MMAs of tile t+2 run under this tile's filter
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[as]);      // this warp is done with the stage
+                if (lane == 0) mbar_arrive(&tempty_bar[as]);
                 if (++as == 2) { as = 0; aphase ^= 1u; }
+                if (last_tile) {
+                    mask_padding(va, tcol, nb32);
+                    mask_padding(vb, tcol + 32, nb32);
+                }
+                wr = filter_chunk(va, tau, tcol, wr);
+                wr = filter_chunk(vb, tau, tcol + 32, wr);
+                cnt = static_cast<int>(wr - row_buf);
                 // Compaction.  A warp that compacts holds up the accumulator ring for everybody, so
                 // compactions are batched: all rows of the CTA compact together after tiles 2, 8, 32,
                 // 128, ... of the unit (the threshold then rises fast enough that a list never fills in
