@@ -475,10 +475,14 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // the tiles: thread `me` takes the tiles that use accumulator stage `me`.
         if (lane == 0) {
             const int me = (warp == kMmaWarp) ? 0 : 1;
+            // (with several K-slabs per tile a thread that skips a whole tile could mistake an older
+            // fill of a ring stage for its own -- same mbarrier parity -- so d > 64 keeps one issuer)
+            const int n_issuers = A_RES ? 2 : 1;
             int64_t cidx = 0;                    // global K-slab counter -> ring stage / phase
             int64_t g = 0;                       // global tile counter -> accumulator stage g & 1
-            uint32_t uphase = 0, aph = 0;
-            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            uint32_t uphase = 0;
+            uint32_t aph[2] = {0u, 0u};
+            for (int unit = blockIdx.x; me < n_issuers && unit < n_units; unit += gridDim.x) {
                 const int sl = unit % a.n_slices;
                 const int t_lo = sl * a.tiles_per_slice;
                 const int t_hi = min(t_lo + a.tiles_per_slice, n_col_tiles);
@@ -488,8 +492,9 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     tc_fence_after();
                 }
                 for (int t = t_lo; t < t_hi; ++t, ++g, cidx += n_kc) {
-                    if ((g & 1) != me) continue;
-                    mbar_wait_backoff(&tempty_bar[me], aph ^ 1u);   // epilogue drained this accumulator stage
+                    if (static_cast<int>(g % n_issuers) != me) continue;
+                    const int as = static_cast<int>(g & 1);
+                    mbar_wait_backoff(&tempty_bar[as], aph[as] ^ 1u);   // epilogue drained this accumulator stage
                     tc_fence_after();
                     for (int kc = 0; kc < n_kc; ++kc) {
                         const int stage = static_cast<int>((cidx + kc) % kStages);
@@ -507,14 +512,14 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                             for (int rb = 0; rb < RB; ++rb) {
                                 // +32 bytes along K inside the 128-byte swizzle row = +2 in the (>>4) address field;
                                 // the next 128-row block of A starts 16 KB (= 1024 in that field) further
-                                umma_bf16(tmem_base + (me * RB + rb) * BN, da + rb * (128 * BK * 2 / 16) + 2 * k, db + 2 * k,
+                                umma_bf16(tmem_base + (as * RB + rb) * BN, da + rb * (128 * BK * 2 / 16) + 2 * k, db + 2 * k,
                                           S::kIdesc, acc);
                             }
                         }
                         umma_commit(&empty_bar[stage]);           // smem stage reusable once these MMAs retire
                     }
-                    umma_commit(&tfull_bar[me]);                  // accumulators complete
-                    aph ^= 1u;
+                    umma_commit(&tfull_bar[as]);                  // accumulators complete
+                    aph[as] ^= 1u;
                 }
                 if (A_RES) umma_commit(aempty_bar);               // my MMAs on the resident A slab have retired
             }
