@@ -730,12 +730,12 @@ constexpr int kRescoreMax = 1024;  // n_slices * kp + K masked (<= 4*128 + 64), 
 constexpr int kRescoreWarps = 4;
 
 // one warp per row
-__global__ void __launch_bounds__(kRescoreWarps * 32) rescore_kernel(const RescoreArgs a) {
-    __shared__ uint64_t keys_all[kRescoreWarps][kRescoreMax];
+__global__ void __launch_bounds__(kRescoreWarps * 32) rescore_kernel(const RescoreArgs a, const int keys_per_warp) {
+    extern __shared__ __align__(16) unsigned char rescore_smem[];   // [kRescoreWarps][keys_per_warp] keys
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = static_cast<int64_t>(blockIdx.x) * kRescoreWarps + wib;
     if (row >= a.Ma) return;
-    uint64_t *keys = keys_all[wib];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(rescore_smem) + static_cast<size_t>(wib) * keys_per_warp;
     const int n_in = a.n_slices * a.kp;
     const float *ar = a.A + row * a.D;
     float tmax = -INFINITY;
@@ -786,7 +786,23 @@ __global__ void __launch_bounds__(kRescoreWarps * 32) rescore_kernel(const Resco
             const uint32_t col = key_index(ak);
             const float *br = a.B + static_cast<int64_t>(col) * a.D;
             float acc = 0.0f;
-            for (int k = 0; k < a.D; k += 4) {                // canonical chain: k ascending, one fmaf per term
+            int k = 0;
+            // canonical chain: k ascending, one fmaf per term.  The lane's candidate row is a private
+            // 4*D-byte stream: eight 16-byte loads (one 128-byte line) are issued before they are consumed.
+            for (; k + 32 <= a.D; k += 32) {
+                float4 y[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) y[u] = __ldg(reinterpret_cast<const float4 *>(br + k) + u);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 x = *reinterpret_cast<const float4 *>(ar + k + 4 * u);
+                    acc = fmaf(x.x, y[u].x, acc);
+                    acc = fmaf(x.y, y[u].y, acc);
+                    acc = fmaf(x.z, y[u].z, acc);
+                    acc = fmaf(x.w, y[u].w, acc);
+                }
+            }
+            for (; k < a.D; k += 4) {
                 const float4 x = *reinterpret_cast<const float4 *>(ar + k);
                 const float4 y = __ldg(reinterpret_cast<const float4 *>(br + k));
                 acc = fmaf(x.x, y.x, acc);
@@ -984,7 +1000,16 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     r.mask_rowptr = e.mask_rowptr; r.mask_col = e.mask_col; r.mask_value = e.mask_value;
     r.id_offset = e.id_offset; r.out_idx = e.out_idx; r.out_score = e.out_score;
     r.fallback_rows = fb_rows; r.fallback_seeds = fb_seeds; r.fallback_count = counters + 16;
-    rescore_kernel<<<static_cast<unsigned>((e.Ma + kRescoreWarps - 1) / kRescoreWarps), kRescoreWarps * 32, 0, stm>>>(r);
+    {
+        // shared-memory keys per warp: the larger of (all published candidates) and (re-scored + masked)
+        int need = r.n_slices * kp;
+        if (need < kp + e.K) need = kp + e.K;
+        int keys_per_warp = 64;
+        while (keys_per_warp < need) keys_per_warp <<= 1;
+        if (keys_per_warp > kRescoreMax) return CHAOREC_E_UNSUPPORTED;
+        rescore_kernel<<<static_cast<unsigned>((e.Ma + kRescoreWarps - 1) / kRescoreWarps), kRescoreWarps * 32,
+                         static_cast<size_t>(kRescoreWarps) * keys_per_warp * 8, stm>>>(r, keys_per_warp);
+    }
     int rc = launch_status();
     if (rc != CHAOREC_OK) return rc;
     // rows that could not be certified: exact CUDA-core engine over the listed rows only
