@@ -272,7 +272,10 @@ def run_eval_leg(args, dev, rank, world, peaks):
     if tensor:
         roof = dict(kernel="tc_candidates_kernel (tcgen05 bf16 pre-filter; time includes bf16 conversion, fp32 re-score + "
                            "certification and the exact fallback launch)", bound="tensor", achieved=achieved,
-                    peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops"], traffic=None,
+                    peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops"],
+                    # dram__bytes_read+write of tc_candidates_kernel<true> at this exact workload on 1 GPU, from the
+                    # ncu --set full capture summarised in profiles/ (3.5 GB read + 8.6 GB written, mostly list appends)
+                    traffic=(12.1e9 if (world == 1 and args.scale == 1.0) else None),
                     peak_source=peaks["source"] + " (bf16 dense burst)", algorithmic_flops_per_launch=flops,
                     kernel_ms=t_rank_kernel * 1e3, fallback_rows=st.get("fallback_rows"),
                     fp32_fma_peak_tflops_measured=fp32_peak)
@@ -376,7 +379,11 @@ def run_propagate_leg(args, dev, rank, world, peaks):
                             users=U, items=I, edges=E, nnz_sym=nnz, d=d, layers=L, hub_rows=graph.n_hub,
                             hub_chunks=graph.n_hub_chunks, l2="inputs (2.7 GB table, 0.8 GB indices) exceed L2", scale=args.scale),
                 roofline=dict(kernel="spmm_rows_kernel<16,1> (+hub kernels)", bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"],
-                              unit="GB/s", frac=achieved / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"],
+                              unit="GB/s", frac=achieved / peaks["hbm_gbs"],
+                              # ncu dram bytes per layer at this workload (profiles/): rows kernel 21.7 GB read + 5.4 GB
+                              # written, hub-chunk kernel 17.6 GB read -> 44.7 GB against 52.9 GB algorithmic (L2 absorbs
+                              # the popular item rows)
+                              traffic=(44.7e9 if args.scale == 1.0 else None), peak_source=peaks["source"],
                               algorithmic_bytes_per_layer=bytes_layer),
                 gpu_launches=(1 + (2 if graph.n_hub else 0)) * L * args.steps)
 
