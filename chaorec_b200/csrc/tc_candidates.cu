@@ -558,10 +558,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             int cnt = 0;
             uint64_t *wr = row_buf;
             for (int t = t_lo; t < t_hi; ++t) {
-                // one lane polls, the warp follows: 512 threads spinning on the same mbarrier word flood the
-                // shared-memory pipe that also feeds the tensor core its operands
-                if (lane == 0) mbar_wait(&tfull_bar[as], aphase);
-                __syncwarp();
+                mbar_wait(&tfull_bar[as], aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * RB + rb) * BN;
                 // 32-column chunks, software-pipelined: the next chunk's tcgen05.ld is in flight while the
