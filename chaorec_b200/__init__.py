@@ -5,15 +5,15 @@ C ABI of ``include/chaorec_b200.h``).  It has no CPU or eager-PyTorch fallback: 
 entry point raises if the library has not been built or the inputs are not CUDA tensors.
 """
 from . import _lib
-from .propagate import (CSRGraph, LightGCNConv, csr_from_coo, csr_from_sparse_coo, graph_from_edge_index,
-                        lightgcn_forward, propagate_mean, spmm)
+from .propagate import (CSRGraph, LightGCNConv, bipartite_graph, csr_from_coo, csr_from_sparse_coo,
+                        graph_from_edge_index, lightgcn_forward, propagate_mean, resample_masked_graph, spmm)
 from .ranking import (MaskCSR, PositivesCSR, build_mask_csr, build_positives_csr, evaluate, evaluate_full,
                       gene_ranklist, hit_masks, mask_csr_from_edges, metrics_from_hits, rank_topk)
 from .knn import (build_knn_neighbourhood, get_knn_adj_mat, knn_laplacian_ones, knn_self_excluded,
                   knn_sym_laplacian, knn_topk, l2_normalize)
 
 __all__ = [
-    "CSRGraph", "LightGCNConv", "csr_from_coo", "csr_from_sparse_coo", "graph_from_edge_index",
+    "CSRGraph", "LightGCNConv", "bipartite_graph", "resample_masked_graph", "csr_from_coo", "csr_from_sparse_coo", "graph_from_edge_index",
     "lightgcn_forward", "propagate_mean", "spmm",
     "MaskCSR", "PositivesCSR", "build_mask_csr", "build_positives_csr", "evaluate", "evaluate_full",
     "gene_ranklist", "hit_masks", "mask_csr_from_edges", "metrics_from_hits", "rank_topk",

@@ -317,3 +317,57 @@ def lightgcn_forward(user_weight: torch.Tensor, item_weight: torch.Tensor, edge_
     """Fused body of ``LightGCN.forward`` (Model/LightGCN.py:76-95)."""
     x0 = torch.cat((user_weight, item_weight), dim=0)
     return propagate_mean(graph_from_edge_index(edge_index, x0.size(0)), x0, n_layers, True)
+
+
+# ---------------------------------------------------------------------------------------------
+# Device-side adjacency builders (SURVEY.md §8f rank 1): the graphs the reference builds on the
+# host with torch / scipy, produced directly as CSRGraph + degree scales.
+# ---------------------------------------------------------------------------------------------
+
+
+def bipartite_graph(users: torch.Tensor, local_items: torch.Tensor, num_user: int, num_item: int,
+                    variant: str = "v1") -> CSRGraph:
+    """Symmetrised (U+I) x (U+I) user-item graph from (user, local item) pairs, normalised on the device.
+
+    variant  reference                                               edge weight
+    -------  ------------------------------------------------------  -----------------------------------
+    "v1"     LightGCNConv, Model/LightGCN.py:36-38                   deg^-1/2[r] * deg^-1/2[c]
+    "v2"     FREEDOM.get_norm_adj_mat, Model/FREEDOM.py:73-83        (2deg)^-1/2[r] * (2deg)^-1/2[c]  (half of v1)
+    "v3"     FREEDOM._normalize_adj_m + mirror, Model/FREEDOM.py:85-100,153-162
+                                                                      (deg+1e-7)^-1/2[r] * (deg+1e-7)^-1/2[c]
+    The weights are never materialised: they are the row/col scales the SpMM kernel applies.
+    """
+    _lib.require_cuda(users, "users")
+    lib = _lib.load()
+    dev = users.device
+    n = num_user + num_item
+    u = users.to(torch.int64)
+    it = local_items.to(torch.int64) + num_user
+    g = csr_from_coo(torch.cat((u, it)), torch.cat((it, u)), None, n, n)
+    dis = torch.empty(n, dtype=torch.float32, device=dev)
+    eps = 1e-7 if variant == "v3" else 0.0
+    with torch.cuda.device(dev):
+        _lib.check(lib.chaorec_degree_inv_sqrt(_lib.ptr(g.rowptr), n, float(eps), _lib.ptr(dis), _lib.stream_ptr(dev)),
+                   "chaorec_degree_inv_sqrt")
+    if variant == "v2":
+        dis = dis * (2.0 ** -0.5)
+    elif variant not in ("v1", "v3"):
+        raise ValueError("variant must be 'v1', 'v2' or 'v3'")
+    g.row_scale = g.col_scale = dis
+    g.symmetric = True
+    return g
+
+
+def resample_masked_graph(edge_users: torch.Tensor, edge_local_items: torch.Tensor, edge_values: torch.Tensor,
+                          num_user: int, num_item: int, dropout: float,
+                          generator: Optional[torch.Generator] = None) -> CSRGraph:
+    """FREEDOM.pre_epoch_processing (Model/FREEDOM.py:143-162) on the device: keep
+    int(E * (1 - dropout)) edges drawn without replacement with probability proportional to their
+    normalised weight, re-normalise the kept block (v3) and mirror it.  (The draw uses the device
+    RNG stream, so kept sets differ from the reference's CPU stream; everything downstream of the
+    kept set is identical.)"""
+    if dropout <= 0.0:
+        return bipartite_graph(edge_users, edge_local_items, num_user, num_item, "v2")   # masked_adj = norm_adj
+    keep_n = int(edge_values.size(0) * (1.0 - dropout))
+    idx = torch.multinomial(edge_values, keep_n, generator=generator)
+    return bipartite_graph(edge_users[idx], edge_local_items[idx], num_user, num_item, "v3")

@@ -233,3 +233,38 @@ def test_hot_column_staging_matches_plain_kernel():
     p32 = cb.propagate_mean(g, x32, 2)
     g._hot[32] = g._hot[d]
     assert torch.equal(cb.propagate_mean(g, x32, 2), p32)
+
+
+def test_device_side_adjacency_builders_match_reference_fixture():
+    """V1/V2/V3 graphs built on the device reproduce the reference's results."""
+    g = load_golden("freedom_small.npz")
+    U, I = int(g["num_user"]), int(g["num_item"])
+    uw, iw = torch.from_numpy(g["user_w"]).to(dev()), torch.from_numpy(g["item_w"]).to(dev())
+    x0 = torch.cat((uw, iw), 0)
+    mm = torch.sparse_coo_tensor(torch.from_numpy(g["mm_adj_idx"]), torch.from_numpy(g["mm_adj_val"]), (I, I)).to(dev())
+    h = cb.spmm(mm, iw)
+    train = torch.from_numpy(g["train"].astype(np.int64)).to(dev())
+    # V2: FREEDOM.norm_adj (halved values)
+    v2 = cb.bipartite_graph(train[:, 0], train[:, 1] - U, U, I, "v2")
+    res = cb.propagate_mean(v2, x0, int(g["n_layers"]))
+    assert rel_err(torch.cat((res[:U], res[U:] + h)), torch.from_numpy(g["result_norm"])) <= REL
+    # V3: the per-epoch masked graph, from the reference's own kept edges
+    midx = torch.from_numpy(g["masked_adj_idx"])
+    keep = midx[:, : midx.shape[1] // 2].to(dev())
+    v3 = cb.bipartite_graph(keep[0], keep[1] - U, U, I, "v3")
+    res = cb.propagate_mean(v3, x0, int(g["n_layers"]))
+    assert rel_err(torch.cat((res[:U], res[U:] + h)), torch.from_numpy(g["result_masked"])) <= REL
+    # V1 == the PyG conv graph
+    l = load_golden("lightgcn_small.npz")
+    U1, I1 = int(l["num_user"]), int(l["num_item"])
+    tr = torch.from_numpy(l["train"].astype(np.int64)).to(dev())
+    v1 = cb.bipartite_graph(tr[:, 0], tr[:, 1] - U1, U1, I1, "v1")
+    x1 = torch.from_numpy(np.concatenate([l["user_w"], l["item_w"]])).to(dev())
+    assert rel_err(cb.propagate_mean(v1, x1, int(l["n_layers"])), torch.from_numpy(l["result"])) <= REL
+    # resampling keeps int(E*(1-p)) distinct edges and renormalises them (structure-level check)
+    vals = torch.ones(train.shape[0], device=dev())
+    rg = cb.resample_masked_graph(train[:, 0], train[:, 1] - U, vals, U, I, 0.3, torch.Generator(device=dev()).manual_seed(1))
+    assert rg.nnz == 2 * int(train.shape[0] * 0.7)
+    deg = (rg.rowptr[1:] - rg.rowptr[:-1]).float()
+    want = (deg + 1e-7).pow(-0.5)          # like the reference, also on empty rows (never indexed)
+    assert torch.allclose(rg.row_scale, want, rtol=1e-6, atol=0)
