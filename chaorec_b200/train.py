@@ -1,0 +1,59 @@
+"""BPR training step around the propagation.
+
+Reference: ``LightGCN.loss`` = ``bpr_loss`` + ``regularization_loss`` (Model/LightGCN.py:97-135),
+driven by ``train_and_evaluate.train`` (train_and_evaluate.py:43-48).  The loss and its gradient
+with respect to the propagated table come from one kernel (csrc/bpr.cu); the backward of the
+propagation is the fused SpMM chain of propagate.py; the optimiser stays torch's.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .propagate import graph_from_edge_index, propagate_mean
+
+
+class _BprLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, users, pos_items, neg_items, reg_weight, item_offset):
+        _lib.require_cuda(emb, "embeddings")
+        lib = _lib.load()
+        emb_c = emb.detach().contiguous()
+        dev = emb_c.device
+        users = users.to(device=dev, dtype=torch.int64).contiguous()
+        pos_items = pos_items.to(device=dev, dtype=torch.int64).contiguous()
+        neg_items = neg_items.to(device=dev, dtype=torch.int64).contiguous()
+        B = int(users.numel())
+        terms = torch.empty(B, dtype=torch.float32, device=dev)
+        grad = torch.zeros_like(emb_c)
+        with torch.cuda.device(dev):
+            rc = lib.chaorec_bpr_loss_grad_f32(_lib.ptr(emb_c), _lib.ptr(users), _lib.ptr(pos_items), _lib.ptr(neg_items), B,
+                                               emb_c.shape[0], emb_c.shape[1], int(item_offset), float(reg_weight),
+                                               _lib.ptr(terms), _lib.ptr(grad), _lib.stream_ptr(dev))
+        _lib.check(rc, "chaorec_bpr_loss_grad_f32")
+        ctx.save_for_backward(grad)
+        return terms.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None, None, None
+
+
+def bpr_loss(embeddings: torch.Tensor, users: torch.Tensor, pos_items: torch.Tensor, neg_items: torch.Tensor,
+             reg_weight: float, num_user: int) -> torch.Tensor:
+    """``bpr_loss + regularization_loss`` of Model/LightGCN.py:97-121 on the propagated table.
+    ``pos_items`` / ``neg_items`` are LOCAL item ids (the reference subtracts num_user first,
+    Model/LightGCN.py:124-125)."""
+    return _BprLossFn.apply(embeddings, users, pos_items, neg_items, float(reg_weight), int(num_user))
+
+
+def lightgcn_loss(user_weight: torch.Tensor, item_weight: torch.Tensor, edge_index: torch.Tensor, n_layers: int,
+                  users: torch.Tensor, pos_items_global: torch.Tensor, neg_items_global: torch.Tensor, reg_weight: float):
+    """Drop-in body of ``LightGCN.loss(users, pos_items, neg_items)`` (Model/LightGCN.py:123-135):
+    returns (total_loss, propagated table); ``total_loss.backward()`` runs the fused backward."""
+    num_user = user_weight.shape[0]
+    x0 = torch.cat((user_weight, item_weight), dim=0)
+    emb = propagate_mean(graph_from_edge_index(edge_index, x0.size(0)), x0, n_layers, True)
+    loss = bpr_loss(emb, users, pos_items_global - num_user, neg_items_global - num_user, reg_weight, num_user)
+    return loss, emb

@@ -103,6 +103,17 @@ int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *col, const fl
                              int32_t n_hub, int64_t n_hub_chunks, float *hub_partials, const int32_t *hot_col_enc,
                              const int32_t *hot_cols, int32_t n_hot, int64_t M, int64_t N, int32_t d, void *stream);
 
+/*
+ * BPR step around the propagation (Model/LightGCN.py:97-135): for B triples (users[b], pos[b], neg[b]),
+ * rows users[b], item_offset+pos[b], item_offset+neg[b] of emb [N, d]:
+ *   loss = -mean log(sigmoid(<u,p> - <u,n>) + 1e-5) + reg_weight * (mean(u^2) + mean(p^2) + mean(n^2))
+ * loss_terms float [B] receives the per-triple shares (their sum is the loss), grad float [N*d]
+ * must be zero-initialised by the caller and receives d loss / d emb (atomic scatter).  d in {32, 64, 128}.
+ */
+int chaorec_bpr_loss_grad_f32(const float *emb, const int64_t *users, const int64_t *pos_items,
+                              const int64_t *neg_items, int64_t B, int64_t N, int32_t d, int64_t item_offset,
+                              float reg_weight, float *loss_terms, float *grad, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * (2) Full-ranking evaluation
  * ---------------------------------------------------------------------------------------- */

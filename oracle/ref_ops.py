@@ -67,6 +67,21 @@ def lightgcn_forward(user_w: torch.Tensor, item_w: torch.Tensor, edge_index: tor
     return out
 
 
+def lightgcn_loss(user_w, item_w, edge_index, n_layers, users, pos_items_global, neg_items_global, reg_weight):
+    """LightGCN.loss, Model/LightGCN.py:97-135: BPR term -mean(log(sigmoid(pos-neg)+1e-5)) plus
+    reg * (mean(u^2) + mean(p^2) + mean(n^2)) on rows of the propagated table (differentiable)."""
+    num_user = user_w.shape[0]
+    pos = pos_items_global - num_user
+    neg = neg_items_global - num_user
+    emb = lightgcn_forward(user_w, item_w, edge_index, n_layers)
+    u, p, n = emb[users], emb[num_user + pos], emb[num_user + neg]
+    pos_s = torch.sum(u * p, dim=1)
+    neg_s = torch.sum(u * n, dim=1)
+    bpr = -torch.mean(torch.log(torch.sigmoid(pos_s - neg_s) + 1e-5))
+    reg = reg_weight * (torch.mean(u ** 2) + torch.mean(p ** 2) + torch.mean(n ** 2))
+    return bpr + reg
+
+
 def freedom_norm_adj(edge_index: torch.Tensor, n_nodes: int) -> torch.Tensor:
     """V2 values, Model/FREEDOM.py:73-83: degree = bincount(cat(row, col)) (twice the true
     degree on the symmetrised list) -> values are half the textbook D^-1/2 A D^-1/2."""

@@ -126,6 +126,31 @@ def lightgcn_case():
         metrics_val=metrics_to_array(m_val, ks), metrics_test=metrics_to_array(m_test, ks))
 
 
+def train_step_case():
+    """One BPR training step of the reference LightGCN (loss + backward), same model as lightgcn_case."""
+    print("LightGCN training step (reference Model/LightGCN.py:97-135 + autograd)")
+    U, I, d, L = 300, 200, 64, 3
+    train, uid, _, _, _, _ = dataset(U, I, 1800, 20261)
+    torch.manual_seed(1234)
+    model = LightGCN(U, I, train, uid, d, 1e-4, L, 'add', 'cpu')
+    with torch.no_grad():
+        model.user_embedding.weight.copy_(ref_ops.normal_embeddings(U, d, 11))
+        model.item_embedding.weight.copy_(ref_ops.normal_embeddings(I, d, 12))
+    g = torch.Generator().manual_seed(99)
+    B = 256
+    pick = torch.randint(0, train.shape[0], (B,), generator=g)
+    users = torch.from_numpy(train[pick.numpy(), 0].astype(np.int64))
+    pos = torch.from_numpy(train[pick.numpy(), 1].astype(np.int64))            # global item ids
+    neg = torch.randint(0, I, (B,), generator=g) + U                          # global item ids
+    users[:8] = users[0]                                                      # repeated rows inside the batch
+    loss = model.loss(users, pos, neg)
+    loss.backward()
+    np.savez_compressed(os.path.join(HERE, "lightgcn_train_step.npz"), num_user=U, num_item=I, n_layers=L, reg_weight=1e-4,
+                        users=users.numpy(), pos=pos.numpy(), neg=neg.numpy(), loss=np.float32(loss.item()),
+                        grad_user=model.user_embedding.weight.grad.numpy(), grad_item=model.item_embedding.weight.grad.numpy())
+    print("  loss", float(loss))
+
+
 def freedom_case():
     print("FREEDOM (reference Model/FREEDOM.py, unchanged)")
     U, I, d = 260, 180, 64
@@ -237,9 +262,11 @@ def real_graph_case():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["lightgcn", "freedom", "metrics", "real"]
+    which = sys.argv[1:] or ["lightgcn", "train", "freedom", "metrics", "real"]
     if "lightgcn" in which:
         lightgcn_case()
+    if "train" in which:
+        train_step_case()
     if "freedom" in which:
         freedom_case()
     if "metrics" in which:

@@ -268,3 +268,26 @@ def test_device_side_adjacency_builders_match_reference_fixture():
     deg = (rg.rowptr[1:] - rg.rowptr[:-1]).float()
     want = (deg + 1e-7).pow(-0.5)          # like the reference, also on empty rows (never indexed)
     assert torch.allclose(rg.row_scale, want, rtol=1e-6, atol=0)
+
+
+def test_bpr_training_step_matches_reference_fixture():
+    """BASELINE configs[1] "BPR step": loss and parameter gradients of the reference LightGCN.loss
+    (Model/LightGCN.py:97-135 + autograd) through the fused forward/backward."""
+    g = load_golden("lightgcn_small.npz")
+    s = load_golden("lightgcn_train_step.npz")
+    uw = torch.from_numpy(g["user_w"]).to(dev()).requires_grad_(True)
+    iw = torch.from_numpy(g["item_w"]).to(dev()).requires_grad_(True)
+    ei = torch.from_numpy(g["edge_index"]).to(dev())
+    loss, emb = cb.lightgcn_loss(uw, iw, ei, int(s["n_layers"]), torch.from_numpy(s["users"]), torch.from_numpy(s["pos"]),
+                                 torch.from_numpy(s["neg"]), float(s["reg_weight"]))
+    loss.backward()
+    assert abs(float(loss) - float(s["loss"])) <= 1e-6 * abs(float(s["loss"]))
+    assert rel_err(uw.grad, torch.from_numpy(s["grad_user"])) <= REL
+    assert rel_err(iw.grad, torch.from_numpy(s["grad_item"])) <= REL
+    assert rel_err(emb, torch.from_numpy(g["result"])) <= REL
+    # one Adam step on top of it stays in step with the reference optimiser (main.py:397)
+    ref_u = torch.from_numpy(g["user_w"]).clone().requires_grad_(True)
+    ref_u.grad = torch.from_numpy(s["grad_user"]).clone()
+    torch.optim.Adam([ref_u], lr=1e-3).step()
+    torch.optim.Adam([uw], lr=1e-3).step()
+    assert rel_err(uw, ref_u.detach()) <= REL
