@@ -12,7 +12,8 @@ time).  One step = one pass over all users: fused score+mask+top-K kernel, hit-m
          kernels, device -> host copy of the hit masks, gather to rank 0 and the sequential fp64
          metric reduction on the host (wall clock between synchronised barriers)
 Secondary legs (reported inside the same JSON line): "propagate" (configs[4]-shaped 3-layer
-normalized-adjacency propagation, edges/s, HBM roofline) and "knn" (configs[2], item rows/s).
+normalized-adjacency propagation, edges/s, HBM roofline), "knn" (configs[2], item rows/s) and "train"
+(configs[1], LightGCN BPR training step, ms/step).
 --impl reference times the oracle's restatement of the reference's CPU path on the host cores.
 """
 from __future__ import annotations
@@ -43,7 +44,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--legs", default="eval,propagate,knn")
+    ap.add_argument("--legs", default="eval,propagate,knn,train")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every workload (debug only; marks the line)")
     ap.add_argument("--cpu-sample-users", type=int, default=None)
     return ap.parse_args()
@@ -473,6 +474,68 @@ def run_knn_leg(args, dev, rank, world, peaks):
     return dict(metric="kNN graph item rows/s", config=dict(workload="cosine kNN graph, clothing-shaped (BASELINE configs[2])"), **out)
 
 
+TRAIN_CFG = dict(U=35_598, I=18_357, E=296_337, d=64, L=3, batch=1024, reg=1e-4, seed=20262)
+
+
+def run_train_leg(args, dev, rank, world, peaks):
+    """BASELINE configs[1]: sports-shaped LightGCN, one BPR training step = fused propagation forward,
+    BPR loss + gradient kernel, fused propagation backward, Adam (torch, fused).  Replicas only at N > 1."""
+    import chaorec_b200 as cb
+    from oracle import ref_ops
+    cfg = TRAIN_CFG
+    U, I, d, L, B = int(cfg["U"] * args.scale), int(cfg["I"] * args.scale), cfg["d"], cfg["L"], cfg["batch"]
+    tu, ti = ref_ops.synth_interactions(U, I, int(cfg["E"] * args.scale), cfg["seed"])
+    ei_cpu = ref_ops.symmetrise_edges(torch.stack((tu, ti + U), 1).numpy())
+    ei = ei_cpu.to(dev)
+    uw = ref_ops.xavier_embeddings(U, d, 1).to(dev).requires_grad_(True)
+    iw = ref_ops.xavier_embeddings(I, d, 2).to(dev).requires_grad_(True)
+    opt = torch.optim.Adam([uw, iw], lr=1e-3, fused=True)
+    g = torch.Generator().manual_seed(5)
+    n_batches = 16
+    pick = torch.randint(0, tu.numel(), (n_batches, B), generator=g)
+    users_h, pos_h = tu[pick], ti[pick] + U
+    neg_h = torch.randint(0, I, (n_batches, B), generator=g) + U
+    users, pos, neg = users_h.to(dev), pos_h.to(dev), neg_h.to(dev)
+
+    def step(i):
+        opt.zero_grad(set_to_none=True)
+        loss, _ = cb.lightgcn_loss(uw, iw, ei, L, users[i % n_batches], pos[i % n_batches], neg[i % n_batches], cfg["reg"])
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    torch.cuda.synchronize()
+    n = max(20, args.steps * 4)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        loss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    nnz = int(ei.shape[1])
+    out = dict(metric="LightGCN BPR training step", ms_per_step=ms, steps_per_s=1e3 / ms, propagate_edges_per_s=nnz * L * 2 / (ms * 1e-3),
+               loss=float(loss), config=dict(workload="LightGCN n_layers=3 d=64, sports-shaped (BASELINE configs[1]): propagation fwd+bwd, "
+                                             "BPR loss+grad kernel, Adam", users=U, items=I, nnz_sym=nnz, batch=B, scale=args.scale),
+               gpu_launches=2 * L + 2)
+    if rank == 0 and world == 1:
+        # CPU baseline: the oracle's restatement of the same step (reference arithmetic) on the host cores
+        cu = ref_ops.xavier_embeddings(U, d, 1).requires_grad_(True)
+        ci = ref_ops.xavier_embeddings(I, d, 2).requires_grad_(True)
+        copt = torch.optim.Adam([cu, ci], lr=1e-3)
+        t0 = time.perf_counter()
+        for i in range(3):
+            copt.zero_grad(set_to_none=True)
+            l = ref_ops.lightgcn_loss(cu, ci, ei_cpu, L, users_h[i], pos_h[i], neg_h[i], cfg["reg"])
+            l.backward()
+            copt.step()
+        out["cpu_baseline"] = dict(value=(time.perf_counter() - t0) / 3 * 1e3, unit="ms/step", cores=torch.get_num_threads(), kind="port",
+                                   sample="3 steps of the same model on the host cores (PyG-form gather/scatter propagation + autograd + Adam)")
+    return out
+
+
 def main_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -498,6 +561,9 @@ def main_ours(args):
     if "knn" in legs:
         torch.cuda.empty_cache()
         line["knn"] = run_knn_leg(args, dev, rank, world, peaks)
+    if "train" in legs:
+        torch.cuda.empty_cache()
+        line["train"] = run_train_leg(args, dev, rank, world, peaks)
     if rank == 0 and world == 1 and job is not None:
         cpu, _ = run_cpu_baseline_eval(job, args.cpu_sample_users or 32768)
         line["cpu_baseline"] = cpu
