@@ -516,7 +516,23 @@ def run_train_leg(args, dev, rank, world, peaks):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     nnz = int(ei.shape[1])
-    out = dict(metric="LightGCN BPR training step", ms_per_step=ms, steps_per_s=1e3 / ms, propagate_edges_per_s=nnz * L * 2 / (ms * 1e-3),
+    # the same step replayed from a CUDA graph (the step is launch-bound at this size)
+    ms_graph = None
+    try:
+        gopt = torch.optim.Adam([uw, iw], lr=1e-3, capturable=True)
+        gstep = cb.GraphedLightGCNStep(uw, iw, ei, L, cfg["reg"], B, gopt)
+        for i in range(3):
+            gstep(users[i], pos[i], neg[i])
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(n):
+            gl = gstep(users[i % n_batches], pos[i % n_batches], neg[i % n_batches])
+        e1.record()
+        torch.cuda.synchronize()
+        ms_graph = e0.elapsed_time(e1) / n
+    except Exception as exc:  # capture support is environment dependent; the eager number stands
+        ms_graph = f"unavailable: {type(exc).__name__}: {exc}"[:200]
+    out = dict(metric="LightGCN BPR training step", ms_per_step=ms, ms_per_step_cuda_graph=ms_graph, steps_per_s=1e3 / ms, propagate_edges_per_s=nnz * L * 2 / (ms * 1e-3),
                loss=float(loss), config=dict(workload="LightGCN n_layers=3 d=64, sports-shaped (BASELINE configs[1]): propagation fwd+bwd, "
                                              "BPR loss+grad kernel, Adam", users=U, items=I, nnz_sym=nnz, batch=B, scale=args.scale),
                gpu_launches=2 * L + 2)

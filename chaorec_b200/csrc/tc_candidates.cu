@@ -74,7 +74,7 @@ struct TcArgs {
     int D;
     int n_row_tiles, n_slices, tiles_per_slice;   // tiles = BN-column tiles
     int kp;                                        // K': candidates kept per (row, slice)
-    int debug_mode;                                // CHAOREC_TC_DEBUG: 1 = no row ever passes the filter, 2 = epilogue skips TMEM loads (timing experiments only; every row then falls back to the exact engine)
+    int debug_mode;                                // CHAOREC_TC_DEBUG bits (timing experiments only): 1 = no row ever passes the filter, 2 = epilogue skips the TMEM loads (either one sends every row to the exact engine), 8 = MMA threads spin instead of suspending
     const int64_t *mask_rowptr;
     const int32_t *mask_col;
     int exclude_self;
@@ -494,6 +494,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 for (int t = t_lo; t < t_hi; ++t, ++g, cidx += n_kc) {
                     if (static_cast<int>(g % n_issuers) != me) continue;
                     const int as = static_cast<int>(g & 1);
+                    if (a.debug_mode >= 8) mbar_wait(&tempty_bar[as], aph[as] ^ 1u); else
                     mbar_wait_backoff(&tempty_bar[as], aph[as] ^ 1u);   // epilogue drained this accumulator stage
                     tc_fence_after();
                     for (int kc = 0; kc < n_kc; ++kc) {
@@ -553,7 +554,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
             // a row whose kept set could not leave room for a tile of appends (a user with hundreds of
             // train items) is not pre-filtered at all: it goes to the exact engine
-            bool give_up = row_ok && ((r_keep + 32 > kTcTrigger) || a.debug_mode != 0);
+            bool give_up = row_ok && ((r_keep + 32 > kTcTrigger) || (a.debug_mode & 3) != 0);
             float tau = (row_ok && !give_up) ? -INFINITY : INFINITY;
             int cnt = 0;
             uint64_t *wr = row_buf;
@@ -569,7 +570,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const uint32_t tcol = static_cast<uint32_t>(t) * BN + ch * 64;
                 uint32_t va[32], vb[32];
                 __syncwarp();
-                if (a.debug_mode == 2) {
+                if (a.debug_mode & 2) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[as]);

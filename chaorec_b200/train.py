@@ -57,3 +57,47 @@ def lightgcn_loss(user_weight: torch.Tensor, item_weight: torch.Tensor, edge_ind
     emb = propagate_mean(graph_from_edge_index(edge_index, x0.size(0)), x0, n_layers, True)
     loss = bpr_loss(emb, users, pos_items_global - num_user, neg_items_global - num_user, reg_weight, num_user)
     return loss, emb
+
+
+class GraphedLightGCNStep:
+    """One LightGCN BPR training step (forward, loss, backward, optimiser) captured in a CUDA graph.
+
+    At the reference's dataset sizes the step is launch-bound (a dozen sub-100-microsecond kernels), so
+    replaying a captured graph removes the host overhead.  Indices are copied into static buffers
+    before each replay; parameters are updated in place by the (capturable) optimiser.
+
+        step = GraphedLightGCNStep(user_emb.weight, item_emb.weight, edge_index, n_layers, reg, batch, opt)
+        loss = step(users, pos_items_global, neg_items_global)     # returns the loss tensor (device)
+    """
+
+    def __init__(self, user_weight, item_weight, edge_index, n_layers: int, reg_weight: float, batch: int,
+                 optimizer: torch.optim.Optimizer, warmup: int = 3):
+        dev = user_weight.device
+        self.uw, self.iw, self.ei, self.L, self.reg, self.opt = user_weight, item_weight, edge_index, n_layers, reg_weight, optimizer
+        self.users = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.pos = torch.full((batch,), user_weight.shape[0], dtype=torch.int64, device=dev)
+        self.neg = torch.full((batch,), user_weight.shape[0], dtype=torch.int64, device=dev)
+        graph_from_edge_index(edge_index, user_weight.shape[0] + item_weight.shape[0])   # build + cache the CSR outside capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager()
+
+    def _eager(self):
+        self.opt.zero_grad(set_to_none=False)
+        loss, _ = lightgcn_loss(self.uw, self.iw, self.ei, self.L, self.users, self.pos, self.neg, self.reg)
+        loss.backward()
+        self.opt.step()
+        return loss
+
+    def __call__(self, users, pos_items_global, neg_items_global):
+        self.users.copy_(users, non_blocking=True)
+        self.pos.copy_(pos_items_global, non_blocking=True)
+        self.neg.copy_(neg_items_global, non_blocking=True)
+        self.graph.replay()
+        return self.loss

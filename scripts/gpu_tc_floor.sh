@@ -8,7 +8,7 @@ U, I, d, K = 151_552, 200_000, 64, 20
 g = torch.Generator(device=dev).manual_seed(1)
 u = torch.randn(U, d, device=dev, generator=g) * 0.1
 it = torch.randn(I, d, device=dev, generator=g) * 0.1
-for mode in ('0', '1', '2', '0'):
+for mode in ('0', '2', '10', '8', '0'):
     os.environ['CHAOREC_TC_DEBUG'] = mode
     cb.rank_topk(u, it, None, K)
     torch.cuda.synchronize()

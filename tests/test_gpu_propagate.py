@@ -291,3 +291,45 @@ def test_bpr_training_step_matches_reference_fixture():
     torch.optim.Adam([ref_u], lr=1e-3).step()
     torch.optim.Adam([uw], lr=1e-3).step()
     assert rel_err(uw, ref_u.detach()) <= REL
+
+
+def test_cuda_graph_training_step_matches_eager():
+    U, I, d, L, B = 500, 400, 64, 2, 128
+    tu, ti = ref_ops.synth_interactions(U, I, 4000, 21)
+    ei = ref_ops.symmetrise_edges(torch.stack((tu, ti + U), 1).numpy()).to(dev())
+    g = torch.Generator().manual_seed(2)
+    batches = [(torch.randint(0, U, (B,), generator=g).to(dev()), (torch.randint(0, I, (B,), generator=g) + U).to(dev()),
+                (torch.randint(0, I, (B,), generator=g) + U).to(dev())) for _ in range(4)]
+
+    def params():
+        return (ref_ops.xavier_embeddings(U, d, 1).to(dev()).requires_grad_(True),
+                ref_ops.xavier_embeddings(I, d, 2).to(dev()).requires_grad_(True))
+
+    uw, iw = params()
+    opt = torch.optim.Adam([uw, iw], lr=1e-2, capturable=True)
+    losses = []
+    for u, p, n in batches:
+        opt.zero_grad(set_to_none=False)
+        loss, _ = cb.lightgcn_loss(uw, iw, ei, L, u, p, n, 1e-4)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    uw2, iw2 = params()
+    opt2 = torch.optim.Adam([uw2, iw2], lr=1e-2, capturable=True)
+    step = cb.GraphedLightGCNStep(uw2, iw2, ei, L, 1e-4, B, opt2, warmup=0)
+    # capture ran the step once on the zero batch: rebuild fresh parameters/optimizer state is not possible
+    # after capture, so compare a second graphed run against an eager run that replays the same history
+    uw3, iw3 = params()
+    opt3 = torch.optim.Adam([uw3, iw3], lr=1e-2, capturable=True)
+    zero = (torch.zeros(B, dtype=torch.int64, device=dev()), torch.full((B,), U, dtype=torch.int64, device=dev()),
+            torch.full((B,), U, dtype=torch.int64, device=dev()))
+    for u, p, n in [zero] + batches:
+        opt3.zero_grad(set_to_none=False)
+        loss, _ = cb.lightgcn_loss(uw3, iw3, ei, L, u, p, n, 1e-4)
+        loss.backward()
+        opt3.step()
+    for u, p, n in batches:
+        gl = step(u, p, n)
+    torch.cuda.synchronize()
+    assert abs(float(gl) - float(loss)) <= 1e-5 * abs(float(loss))
+    assert rel_err(uw2, uw3.detach()) <= 1e-4 and rel_err(iw2, iw3.detach()) <= 1e-4
