@@ -519,8 +519,10 @@ def run_train_leg(args, dev, rank, world, peaks):
     # the same step replayed from a CUDA graph (the step is launch-bound at this size)
     ms_graph = None
     try:
-        gopt = torch.optim.Adam([uw, iw], lr=1e-3, capturable=True)
-        gstep = cb.GraphedLightGCNStep(uw, iw, ei, L, cfg["reg"], B, gopt)
+        # fresh leaves: the eager steps above tied uw/iw's gradient accumulators to the default stream
+        guw, giw = uw.detach().clone().requires_grad_(True), iw.detach().clone().requires_grad_(True)
+        gopt = torch.optim.Adam([guw, giw], lr=1e-3, capturable=True)
+        gstep = cb.GraphedLightGCNStep(guw, giw, ei, L, cfg["reg"], B, gopt)
         for i in range(3):
             gstep(users[i], pos[i], neg[i])
         torch.cuda.synchronize()
@@ -531,6 +533,8 @@ def run_train_leg(args, dev, rank, world, peaks):
         torch.cuda.synchronize()
         ms_graph = e0.elapsed_time(e1) / n
     except Exception as exc:  # capture support is environment dependent; the eager number stands
+        import traceback
+        traceback.print_exc(file=sys.stderr)
         ms_graph = f"unavailable: {type(exc).__name__}: {exc}"[:200]
     out = dict(metric="LightGCN BPR training step", ms_per_step=ms, ms_per_step_cuda_graph=ms_graph, steps_per_s=1e3 / ms, propagate_edges_per_s=nnz * L * 2 / (ms * 1e-3),
                loss=float(loss), config=dict(workload="LightGCN n_layers=3 d=64, sports-shaped (BASELINE configs[1]): propagation fwd+bwd, "

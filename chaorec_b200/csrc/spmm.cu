@@ -20,8 +20,17 @@ namespace chaorec {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kHubThreshold = 1024;
+constexpr int kHubThreshold = 1024;   // defaults (large graphs); chaorec_spmm_hub_plan scales them down
 constexpr int kHubChunk = 4096;
+constexpr int kHubMaxChunksPerRow = 64;
+
+// Edges per chunk of a hub row with `deg` edges: at least `hub_chunk`, grown (in steps of 64) so that no
+// row has more than kHubMaxChunksPerRow chunks -- the finish kernel then sums at most that many partials.
+// The host plan (propagate.py: CSRGraph.plan_hubs) computes the same number.
+__host__ __device__ __forceinline__ int64_t hub_chunk_edges(int64_t deg, int hub_chunk) {
+    const int64_t per = (deg + kHubMaxChunksPerRow - 1) / kHubMaxChunksPerRow;
+    return per > hub_chunk ? (per + 63) / 64 * 64 : hub_chunk;
+}
 
 struct SpmmArgs {
     const int64_t *rowptr;
@@ -37,7 +46,11 @@ struct SpmmArgs {
     const int32_t *hub_rows;
     const int64_t *hub_chunk_ptr;
     int n_hub;
+    int hub_threshold;   // rows with more edges than this belong to the hub kernels
+    int hub_chunk;       // minimum edges per hub chunk (see hub_chunk_edges)
     float4 *hub_partials;
+    int *hub_counters;   // non-null: single-launch mode, the last chunk CTA of a row finishes it
+    int64_t n_hub_chunks;
     int64_t M;
     int dq;  // d / 4
 };
@@ -174,20 +187,25 @@ __device__ __forceinline__ void row_epilogue(const SpmmArgs &a, int64_t r, int g
 }
 
 template <int LANES, int NV>
-__global__ void __launch_bounds__(kThreads) spmm_rows_kernel(const SpmmArgs a) {
+__device__ __forceinline__ void rows_body(const SpmmArgs &a, int64_t block) {
     constexpr int kGroups = kThreads / LANES;
     const int lane = threadIdx.x & 31;
     const int gl = threadIdx.x % LANES;
-    const int64_t r = static_cast<int64_t>(blockIdx.x) * kGroups + threadIdx.x / LANES;
+    const int64_t r = block * kGroups + threadIdx.x / LANES;
     if (r >= a.M) return;
     const unsigned mask = group_mask<LANES>(lane);
     const int64_t e_lo = __ldg(a.rowptr + r), e_hi = __ldg(a.rowptr + r + 1);
-    if (a.hub_rows != nullptr && e_hi - e_lo > kHubThreshold) return;  // taken by the hub kernels
+    if (a.hub_rows != nullptr && e_hi - e_lo > a.hub_threshold) return;  // taken by the hub kernels
     float4 acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     gather_edges<LANES, NV, false>(a, e_lo, e_hi, gl, mask, acc);
     row_epilogue<LANES, NV>(a, r, gl, acc);
+}
+
+template <int LANES, int NV>
+__global__ void __launch_bounds__(kThreads) spmm_rows_kernel(const SpmmArgs a) {
+    rows_body<LANES, NV>(a, blockIdx.x);
 }
 
 // Short rows (a user's ~12 items) are latency-bound when a sub-warp walks them one at a time:
@@ -213,11 +231,11 @@ __global__ void __launch_bounds__(kThreads) spmm_rows_seg_kernel(const SpmmArgs 
     float4 acc[NV];
     // a block that contains a hub row (taken by the hub kernels) falls back to row-at-a-time
     const int64_t mydeg = __shfl_down_sync(mask, myptr, 1, LANES) - myptr;
-    const bool has_hub = a.hub_rows != nullptr && __any_sync(mask, gl < nrows && mydeg > kHubThreshold);
+    const bool has_hub = a.hub_rows != nullptr && __any_sync(mask, gl < nrows && mydeg > a.hub_threshold);
     if (has_hub) {
         for (int i = 0; i < nrows; ++i) {
             const int64_t lo = __shfl_sync(mask, myptr, i, LANES), hi = __shfl_sync(mask, myptr, i + 1, LANES);
-            if (hi - lo > kHubThreshold) continue;
+            if (hi - lo > a.hub_threshold) continue;
 #pragma unroll
             for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
             gather_edges<LANES, NV, false>(a, lo, hi, gl, mask, acc);
@@ -334,7 +352,7 @@ __global__ void __launch_bounds__(1024, 1) spmm_rows_hot_kernel(const SpmmArgs a
     __syncthreads();
     for (int64_t r = static_cast<int64_t>(blockIdx.x) * kGroups + g; r < a.M; r += static_cast<int64_t>(gridDim.x) * kGroups) {
         const int64_t e_lo = __ldg(a.rowptr + r), e_hi = __ldg(a.rowptr + r + 1);
-        if (a.hub_rows != nullptr && e_hi - e_lo > kHubThreshold) continue;   // taken by the hub kernels
+        if (a.hub_rows != nullptr && e_hi - e_lo > a.hub_threshold) continue;   // taken by the hub kernels
         float4 acc[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -392,16 +410,47 @@ __global__ void __launch_bounds__(1024, 1) spmm_rows_hot_kernel(const SpmmArgs a
     }
 }
 
+// Sum the partial rows of hub row h in chunk order and apply the row epilogue (one sub-warp).
+template <int LANES, int NV>
+__device__ __forceinline__ void hub_finish_row(const SpmmArgs &a, int h, int gl) {
+    const int64_t r = __ldg(a.hub_rows + h);
+    const int64_t c_lo = __ldg(a.hub_chunk_ptr + h), c_hi = __ldg(a.hub_chunk_ptr + h + 1);
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const int q = gl + v * LANES;
+        if (q >= a.dq) continue;
+        int64_t c = c_lo;
+        for (; c + 8 <= c_hi; c += 8) {          // eight independent partial loads in flight, summed in chunk order
+            float4 p[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p[j] = __ldcg(a.hub_partials + (c + j) * a.dq + q);   // written by other SMs: L2
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[v].x += p[j].x; acc[v].y += p[j].y; acc[v].z += p[j].z; acc[v].w += p[j].w; }
+        }
+        for (; c < c_hi; ++c) {
+            const float4 p = __ldcg(a.hub_partials + c * a.dq + q);
+            acc[v].x += p.x; acc[v].y += p.y; acc[v].z += p.z; acc[v].w += p.w;
+        }
+    }
+    row_epilogue<LANES, NV>(a, r, gl, acc);
+}
+
 // One CTA per (hub row, chunk): every sub-warp reduces a contiguous slice of the chunk, the
 // slices are summed in slice order through shared memory and stored as one partial row.
+// Single-launch mode (a.hub_counters): the CTA that completes a row's last outstanding chunk
+// sums the row's partials (in chunk order, so the result does not depend on which CTA that is)
+// and resets the counter for the next launch.
 template <int LANES, int NV>
-__global__ void __launch_bounds__(kThreads) spmm_hub_chunk_kernel(const SpmmArgs a) {
+__device__ __forceinline__ void hub_chunk_body(const SpmmArgs &a, int64_t chunk) {
     constexpr int kGroups = kThreads / LANES;
     __shared__ float4 part[kGroups][LANES * NV];
+    __shared__ int is_last;
     const int lane = threadIdx.x & 31;
     const int gl = threadIdx.x % LANES;
     const int g = threadIdx.x / LANES;
-    const int64_t chunk = blockIdx.x;
     // hub row h with hub_chunk_ptr[h] <= chunk < hub_chunk_ptr[h+1]
     int lo = 0, hi = a.n_hub;
     while (hi - lo > 1) {
@@ -411,9 +460,10 @@ __global__ void __launch_bounds__(kThreads) spmm_hub_chunk_kernel(const SpmmArgs
     const int64_t r = __ldg(a.hub_rows + lo);
     const int64_t c_in_row = chunk - __ldg(a.hub_chunk_ptr + lo);
     const int64_t row_lo = __ldg(a.rowptr + r), row_hi = __ldg(a.rowptr + r + 1);
-    const int64_t c_lo = row_lo + c_in_row * kHubChunk;
-    const int64_t c_hi = (c_lo + kHubChunk < row_hi) ? c_lo + kHubChunk : row_hi;
-    constexpr int kSlice = kHubChunk / kGroups;
+    const int64_t chunk_edges = hub_chunk_edges(row_hi - row_lo, a.hub_chunk);
+    const int64_t c_lo = row_lo + c_in_row * chunk_edges;
+    const int64_t c_hi = (c_lo + chunk_edges < row_hi) ? c_lo + chunk_edges : row_hi;
+    const int64_t kSlice = (chunk_edges + kGroups - 1) / kGroups;
     int64_t e_lo = c_lo + static_cast<int64_t>(g) * kSlice;
     int64_t e_hi = e_lo + kSlice;
     if (e_lo > c_hi) e_lo = c_hi;
@@ -434,6 +484,24 @@ __global__ void __launch_bounds__(kThreads) spmm_hub_chunk_kernel(const SpmmArgs
         }
         a.hub_partials[chunk * a.dq + q] = s;
     }
+    if (a.hub_counters == nullptr) return;
+    __threadfence();                       // this CTA's partial row is visible device-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) {                // ... before its arrival is counted
+        const int n_chunks = static_cast<int>(__ldg(a.hub_chunk_ptr + lo + 1) - __ldg(a.hub_chunk_ptr + lo));
+        const int prev = atomicAdd(a.hub_counters + lo, 1);
+        is_last = (prev == n_chunks - 1);
+        if (is_last) a.hub_counters[lo] = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (g == 0) hub_finish_row<LANES, NV>(a, lo, gl);
+}
+
+template <int LANES, int NV>
+__global__ void __launch_bounds__(kThreads) spmm_hub_chunk_kernel(const SpmmArgs a) {
+    hub_chunk_body<LANES, NV>(a, blockIdx.x);
 }
 
 template <int LANES, int NV>
@@ -442,22 +510,18 @@ __global__ void __launch_bounds__(kThreads) spmm_hub_finish_kernel(const SpmmArg
     const int gl = threadIdx.x % LANES;
     const int h = blockIdx.x * kGroups + threadIdx.x / LANES;
     if (h >= a.n_hub) return;
-    const int64_t r = __ldg(a.hub_rows + h);
-    const int64_t c_lo = __ldg(a.hub_chunk_ptr + h), c_hi = __ldg(a.hub_chunk_ptr + h + 1);
-    float4 acc[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t c = c_lo; c < c_hi; ++c) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            const int q = gl + v * LANES;
-            if (q < a.dq) {
-                const float4 p = a.hub_partials[c * a.dq + q];
-                acc[v].x += p.x; acc[v].y += p.y; acc[v].z += p.z; acc[v].w += p.w;
-            }
-        }
+    hub_finish_row<LANES, NV>(a, h, gl);
+}
+
+// Single launch for small graphs: the hub-chunk CTAs come first in the grid (they are the long ones), the
+// row CTAs follow; rows are finished by the last chunk CTA (hub_counters), so nothing waits on a second launch.
+template <int LANES, int NV>
+__global__ void __launch_bounds__(kThreads) spmm_fused_kernel(const SpmmArgs a) {
+    if (static_cast<int64_t>(blockIdx.x) < a.n_hub_chunks) {
+        hub_chunk_body<LANES, NV>(a, blockIdx.x);
+        return;
     }
-    row_epilogue<LANES, NV>(a, r, gl, acc);
+    rows_body<LANES, NV>(a, static_cast<int64_t>(blockIdx.x) - a.n_hub_chunks);
 }
 
 template <int LANES, int NV>
@@ -477,13 +541,19 @@ int launch_spmm(const SpmmArgs &a, const HotArgs &h, int64_t n_hub_chunks, cudaS
     if constexpr (LANES > kRowsPerGroup && false) {   // measured slower (80 regs, 10.1 ms vs 8.5 ms at the 100M-edge config)
         const int64_t seg_blocks = (a.M + static_cast<int64_t>(kGroups) * kRowsPerGroup - 1) / (static_cast<int64_t>(kGroups) * kRowsPerGroup);
         if (seg_blocks > 0) spmm_rows_seg_kernel<LANES, NV><<<static_cast<unsigned>(seg_blocks), kThreads, 0, st>>>(a);
+    } else if (a.hub_counters != nullptr && a.hub_rows != nullptr && n_hub_chunks > 0) {
+        if (blocks + n_hub_chunks > 0x7fffffffLL) return CHAOREC_E_UNSUPPORTED;
+        spmm_fused_kernel<LANES, NV><<<static_cast<unsigned>(blocks + n_hub_chunks), kThreads, 0, st>>>(a);
+        return launch_status();
     } else {
         if (blocks > 0) spmm_rows_kernel<LANES, NV><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(a);
     }
     if (a.hub_rows != nullptr && a.n_hub > 0 && n_hub_chunks > 0) {
         if (n_hub_chunks > 0x7fffffffLL) return CHAOREC_E_UNSUPPORTED;
-        spmm_hub_chunk_kernel<LANES, NV><<<static_cast<unsigned>(n_hub_chunks), kThreads, 0, st>>>(a);
-        spmm_hub_finish_kernel<LANES, NV><<<(a.n_hub + kGroups - 1) / kGroups, kThreads, 0, st>>>(a);
+        SpmmArgs b = a;
+        b.hub_counters = nullptr;          // rows are finished by the finish kernel, not by the last chunk CTA
+        spmm_hub_chunk_kernel<LANES, NV><<<static_cast<unsigned>(n_hub_chunks), kThreads, 0, st>>>(b);
+        spmm_hub_finish_kernel<LANES, NV><<<(a.n_hub + kGroups - 1) / kGroups, kThreads, 0, st>>>(b);
     }
     return launch_status();
 }
@@ -507,6 +577,24 @@ using namespace chaorec;
 extern "C" int32_t chaorec_spmm_hub_threshold(void) { return kHubThreshold; }
 extern "C" int32_t chaorec_spmm_hub_chunk(void) { return kHubChunk; }
 
+extern "C" int chaorec_spmm_hub_plan(int64_t nnz, int32_t *threshold, int32_t *chunk) {
+    if (!threshold || !chunk || nnz < 0) return CHAOREC_E_BADARG;
+    // A sub-warp walks its row four gathers at a time (~0.15 us per edge when nothing else hides the
+    // latency), so the longest sub-warp row sets the kernel's tail.  Keep that tail near 1/8 of the
+    // bandwidth-bound kernel time (nnz / 16 G edges/s): threshold ~ nnz / 16384, a power of two in [64, 1024].
+    int t = 64;
+    while (t < kHubThreshold && static_cast<int64_t>(t) * 2 * 16384 <= nnz) t *= 2;
+    *threshold = t;
+    *chunk = 4 * t;
+    return CHAOREC_OK;
+}
+
+extern "C" int64_t chaorec_spmm_hub_row_chunks(int64_t row_nnz, int32_t chunk) {
+    if (row_nnz <= 0 || chunk <= 0) return 0;
+    const int64_t ce = hub_chunk_edges(row_nnz, chunk);
+    return (row_nnz + ce - 1) / ce;
+}
+
 extern "C" int chaorec_degree_inv_sqrt(const int64_t *rowptr, int64_t M, float eps, float *out, void *stream) {
     if (!rowptr || !out || M < 0) return CHAOREC_E_BADARG;
     if (M == 0) return CHAOREC_OK;
@@ -520,7 +608,8 @@ extern "C" int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *co
                                         const float *row_scale, const float *col_scale, const float *x, float *y,
                                         float *acc, float alpha, int32_t acc_mode, const int32_t *hub_rows,
                                         const int64_t *hub_chunk_ptr, int32_t n_hub, int64_t n_hub_chunks,
-                                        float *hub_partials, const int32_t *hot_col_enc, const int32_t *hot_cols,
+                                        int32_t hub_threshold, int32_t hub_chunk, float *hub_partials,
+                                        int32_t *hub_counters, const int32_t *hot_col_enc, const int32_t *hot_cols,
                                         int32_t n_hot, int64_t M, int64_t N, int32_t d, void *stream) {
     if (!rowptr || !x || M < 0 || N < 0 || d <= 0) return CHAOREC_E_BADARG;
     if (!y && !acc) return CHAOREC_E_BADARG;
@@ -530,6 +619,7 @@ extern "C" int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *co
     if (!aligned16(x) || (y && !aligned16(y)) || (acc && !aligned16(acc))) return CHAOREC_E_ALIGN;
     if (hub_rows && n_hub > 0 && (!hub_chunk_ptr || !hub_partials || !aligned16(hub_partials)))
         return CHAOREC_E_BADARG;
+    if (hub_threshold < 0 || hub_chunk < 0) return CHAOREC_E_BADARG;
     if (M == 0) return CHAOREC_OK;
     if (!col) return CHAOREC_E_BADARG;
     SpmmArgs a;
@@ -541,6 +631,10 @@ extern "C" int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *co
     a.hub_rows = (hub_rows && n_hub > 0) ? hub_rows : nullptr;
     a.hub_chunk_ptr = hub_chunk_ptr; a.n_hub = a.hub_rows ? n_hub : 0;
     a.hub_partials = reinterpret_cast<float4 *>(hub_partials);
+    a.hub_counters = a.hub_rows ? hub_counters : nullptr;
+    a.n_hub_chunks = a.hub_rows ? n_hub_chunks : 0;
+    a.hub_threshold = hub_threshold > 0 ? hub_threshold : kHubThreshold;
+    a.hub_chunk = hub_chunk > 0 ? hub_chunk : kHubChunk;
     a.M = M; a.dq = d / 4;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     HotArgs h{};
@@ -560,8 +654,9 @@ extern "C" int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, c
                                     const float *row_scale, const float *col_scale, const float *x, float *y,
                                     float *acc, float alpha, int32_t acc_mode, const int32_t *hub_rows,
                                     const int64_t *hub_chunk_ptr, int32_t n_hub, int64_t n_hub_chunks,
-                                    float *hub_partials, int64_t M, int64_t N, int32_t d, void *stream) {
+                                    int32_t hub_threshold, int32_t hub_chunk, float *hub_partials,
+                                    int32_t *hub_counters, int64_t M, int64_t N, int32_t d, void *stream) {
     return chaorec_spmm_csr_hot_f32(rowptr, col, val, row_scale, col_scale, x, y, acc, alpha, acc_mode, hub_rows,
-                                    hub_chunk_ptr, n_hub, n_hub_chunks, hub_partials, nullptr, nullptr, 0, M, N, d,
-                                    stream);
+                                    hub_chunk_ptr, n_hub, n_hub_chunks, hub_threshold, hub_chunk, hub_partials,
+                                    hub_counters, nullptr, nullptr, 0, M, N, d, stream);
 }

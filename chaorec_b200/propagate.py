@@ -9,6 +9,7 @@ Host logic only; all arithmetic runs in csrc/spmm.cu through the C ABI.
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 import weakref
 from dataclasses import dataclass, field
@@ -33,6 +34,10 @@ class CSRGraph:
     hub_chunk_ptr: Optional[torch.Tensor] = None  # int64 [n_hub+1]
     n_hub: int = 0
     n_hub_chunks: int = 0
+    hub_threshold: int = 0                     # 0 = library default
+    hub_chunk: int = 0
+    hub_counters: Optional[torch.Tensor] = None   # int32 [n_hub] (single-launch mode), kept zero by the kernel
+    SINGLE_LAUNCH_MAX_NNZ = 1 << 24
     _partials: Dict[int, torch.Tensor] = field(default_factory=dict)
     _hot: Dict[int, Optional[Tuple[torch.Tensor, torch.Tensor]]] = field(default_factory=dict)
     _transposed: Optional["CSRGraph"] = None
@@ -46,21 +51,38 @@ class CSRGraph:
     def device(self) -> torch.device:
         return self.rowptr.device
 
-    def plan_hubs(self) -> "CSRGraph":
+    def plan_hubs(self, threshold: Optional[int] = None, chunk: Optional[int] = None) -> "CSRGraph":
+        """Choose which rows the CTA-per-chunk hub kernels take.  Default: the library's plan for this
+        edge count (small graphs get a low threshold: at 0.5M edges one 1000-edge row walked by a single
+        sub-warp would take 150 us of a kernel that otherwise needs ~10)."""
         lib = _lib.load()
-        thr, chunk = lib.chaorec_spmm_hub_threshold(), lib.chaorec_spmm_hub_chunk()
+        if threshold is None or chunk is None:
+            t, c = C.c_int32(0), C.c_int32(0)
+            _lib.check(lib.chaorec_spmm_hub_plan(self.nnz, C.byref(t), C.byref(c)), "chaorec_spmm_hub_plan")
+            threshold = t.value if threshold is None else threshold
+            chunk = c.value if chunk is None else chunk
+        self.hub_threshold, self.hub_chunk = int(threshold), int(chunk)
         deg = self.rowptr[1:] - self.rowptr[:-1]
-        hubs = torch.nonzero(deg > thr).flatten()
+        hubs = torch.nonzero(deg > self.hub_threshold).flatten()
         self.n_hub = int(hubs.numel())
         if self.n_hub:
-            chunks = (deg[hubs] + (chunk - 1)) // chunk
+            hdeg = deg[hubs]
+            # edges per chunk of a row: at least `chunk`, grown in steps of 64 so that a row has <= 64 chunks
+            # (chaorec_spmm_hub_row_chunks, csrc/spmm.cu: hub_chunk_edges)
+            per = (hdeg + 63) // 64
+            chunk_edges = torch.where(per > self.hub_chunk, (per + 63) // 64 * 64, torch.full_like(per, self.hub_chunk))
+            chunks = (hdeg + chunk_edges - 1) // chunk_edges
             ptr = torch.zeros(self.n_hub + 1, dtype=torch.int64, device=self.device)
             ptr[1:] = torch.cumsum(chunks, 0)
             self.hub_rows = hubs.to(torch.int32).contiguous()
             self.hub_chunk_ptr = ptr
             self.n_hub_chunks = int(ptr[-1].item())
+            # small graphs: one launch per product (the kernel time is a few microseconds, two more launches
+            # would double it); large graphs keep the separate kernels (fewer registers in the row kernel)
+            self.hub_counters = (torch.zeros(self.n_hub, dtype=torch.int32, device=self.device)
+                                 if self.nnz < self.SINGLE_LAUNCH_MAX_NNZ else None)
         else:
-            self.hub_rows, self.hub_chunk_ptr, self.n_hub_chunks = None, None, 0
+            self.hub_rows, self.hub_chunk_ptr, self.n_hub_chunks, self.hub_counters = None, None, 0, None
         self._partials.clear()
         return self
 
@@ -168,7 +190,8 @@ def _spmm_raw(g: CSRGraph, x: torch.Tensor, y: Optional[torch.Tensor], acc: Opti
         rc = lib.chaorec_spmm_csr_hot_f32(
             _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.val), _lib.ptr(g.row_scale), _lib.ptr(g.col_scale),
             _lib.ptr(x), _lib.ptr(y), _lib.ptr(acc), float(alpha), int(acc_mode), _lib.ptr(g.hub_rows),
-            _lib.ptr(g.hub_chunk_ptr), g.n_hub, g.n_hub_chunks, _lib.ptr(g.partials(d)),
+            _lib.ptr(g.hub_chunk_ptr), g.n_hub, g.n_hub_chunks, g.hub_threshold, g.hub_chunk, _lib.ptr(g.partials(d)),
+            _lib.ptr(g.hub_counters),
             _lib.ptr(hot[0]) if hot else None, _lib.ptr(hot[1]) if hot else None, int(hot[1].numel()) if hot else 0,
             g.M, g.N, d, _lib.stream_ptr(x.device))
     _lib.check(rc, "chaorec_spmm_csr_hot_f32")

@@ -78,11 +78,22 @@ class GraphedLightGCNStep:
         self.pos = torch.full((batch,), user_weight.shape[0], dtype=torch.int64, device=dev)
         self.neg = torch.full((batch,), user_weight.shape[0], dtype=torch.int64, device=dev)
         graph_from_edge_index(edge_index, user_weight.shape[0] + item_weight.shape[0])   # build + cache the CSR outside capture
+        # Warm-up runs real steps on a side stream (it creates .grad, the optimiser state and every cached
+        # work buffer outside the capture); parameters are then restored and the optimiser state zeroed, so
+        # the first replay is step 1 of a fresh optimiser.
+        saved = [user_weight.detach().clone(), item_weight.detach().clone()]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(warmup):
+            for _ in range(max(1, warmup)):
                 self._eager()
+            with torch.no_grad():
+                user_weight.copy_(saved[0])
+                item_weight.copy_(saved[1])
+                for st in optimizer.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):

@@ -61,9 +61,16 @@ int chaorec_coo_to_csr(const int64_t *row, const int64_t *col, const float *val,
  */
 int chaorec_degree_inv_sqrt(const int64_t *rowptr, int64_t M, float eps, float *out, void *stream);
 
-/* Rows with more than this many non-zeros are "hub rows"; see chaorec_spmm_csr_f32. */
+/* Rows with more than `threshold` non-zeros are "hub rows"; see chaorec_spmm_csr_f32.  The two
+ * no-argument calls return the defaults (used when 0 is passed); chaorec_spmm_hub_plan returns the
+ * values recommended for a graph with nnz edges (smaller graphs get a lower threshold so that one long
+ * row cannot dominate a kernel that otherwise takes microseconds); chaorec_spmm_hub_row_chunks is
+ * the number of chunks a hub row of row_nnz edges is split into for a given `chunk` (host helper:
+ * hub_chunk_ptr is the exclusive prefix sum of it over hub_rows). */
 int32_t chaorec_spmm_hub_threshold(void);
 int32_t chaorec_spmm_hub_chunk(void);
+int chaorec_spmm_hub_plan(int64_t nnz, int32_t *threshold, int32_t *chunk);
+int64_t chaorec_spmm_hub_row_chunks(int64_t row_nnz, int32_t chunk);
 
 /*
  * CSR SpMM, fp32.  Replaces torch.sparse.mm(adj, x) (Model/FREEDOM.py:168,174 and the 36
@@ -76,18 +83,22 @@ int32_t chaorec_spmm_hub_chunk(void);
  * Model/FREEDOM.py:177-178): if acc != NULL
  *     acc_mode 0:  acc[r,:] += alpha * y[r,:]
  *     acc_mode 1:  acc[r,:]  = alpha * x[r,:] + alpha * y[r,:]     (first layer; needs M == N)
- * Hub rows (nnz > chaorec_spmm_hub_threshold()) are split into chunks of
- * chaorec_spmm_hub_chunk() edges reduced through shared memory by whole CTAs: pass the
- * sorted list hub_rows[n_hub], hub_chunk_ptr[n_hub+1] (exclusive prefix of per-row chunk
- * counts) and hub_partials (float [hub_chunk_ptr[n_hub] * d]).  With hub_rows == NULL every
- * row takes the sub-warp path (correct, slow for very long rows).
+ * Hub rows (nnz > hub_threshold) are split into chunks of at least hub_chunk edges (at most 64
+ * chunks per row, chaorec_spmm_hub_row_chunks) reduced through shared memory by whole CTAs: pass
+ * the sorted list hub_rows[n_hub], hub_chunk_ptr[n_hub+1] (exclusive prefix of per-row chunk
+ * counts) and hub_partials (float [hub_chunk_ptr[n_hub] * d]).  hub_threshold / hub_chunk = 0 mean
+ * the defaults.  hub_counters (nullable, int32 [n_hub], zero before the first call; the kernel leaves
+ * it zero) selects the single-launch mode meant for small graphs: row CTAs and hub-chunk CTAs share one
+ * grid and the CTA that completes a hub row's last chunk sums its partials (in chunk order: results do
+ * not depend on scheduling).  Without it hub rows take two extra launches.  With hub_rows == NULL
+ * every row takes the sub-warp path (correct, slow for very long rows).
  * d must be a multiple of 4 and <= 512; x, y, acc 16-byte aligned.
  */
 int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float *val, const float *row_scale,
                          const float *col_scale, const float *x, float *y, float *acc, float alpha,
                          int32_t acc_mode, const int32_t *hub_rows, const int64_t *hub_chunk_ptr,
-                         int32_t n_hub, int64_t n_hub_chunks, float *hub_partials, int64_t M, int64_t N,
-                         int32_t d, void *stream);
+                         int32_t n_hub, int64_t n_hub_chunks, int32_t hub_threshold, int32_t hub_chunk,
+                         float *hub_partials, int32_t *hub_counters, int64_t M, int64_t N, int32_t d, void *stream);
 
 /*
  * Same product with hot-column staging: hot_col_enc int32 [nnz] is `col` with the n_hot most
@@ -100,7 +111,8 @@ int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float 
 int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *col, const float *val, const float *row_scale,
                              const float *col_scale, const float *x, float *y, float *acc, float alpha,
                              int32_t acc_mode, const int32_t *hub_rows, const int64_t *hub_chunk_ptr,
-                             int32_t n_hub, int64_t n_hub_chunks, float *hub_partials, const int32_t *hot_col_enc,
+                             int32_t n_hub, int64_t n_hub_chunks, int32_t hub_threshold, int32_t hub_chunk,
+                             float *hub_partials, int32_t *hub_counters, const int32_t *hot_col_enc,
                              const int32_t *hot_cols, int32_t n_hot, int64_t M, int64_t N, int32_t d, void *stream);
 
 /*

@@ -36,6 +36,13 @@ def test_abi_version_and_error_strings():
     for code in (-1, -2, -3, -4, -5):
         assert len(lib.chaorec_error_string(code)) > 4
     assert lib.chaorec_spmm_hub_chunk() >= lib.chaorec_spmm_hub_threshold() > 0
+    import ctypes
+    t, c = ctypes.c_int32(0), ctypes.c_int32(0)
+    for nnz, want in ((0, 64), (562_350, 64), (4_000_000, 128), (20_000_000, 1024), (200_000_000, 1024)):
+        assert lib.chaorec_spmm_hub_plan(nnz, ctypes.byref(t), ctypes.byref(c)) == 0
+        assert (t.value, c.value) == (want, 4 * want)
+    assert lib.chaorec_spmm_hub_row_chunks(30_000, 256) == 59       # ceil(30000/64)=469 -> 512-edge chunks
+    assert lib.chaorec_spmm_hub_row_chunks(4097, 4096) == 2 and lib.chaorec_spmm_hub_row_chunks(100, 256) == 1
 
 
 def test_no_cpu_fallback():
