@@ -379,7 +379,7 @@ def run_propagate_leg(args, dev, rank, world, peaks):
                 config=dict(workload="3-layer normalized-adjacency propagation + layer mean (BASELINE configs[4] shape)",
                             users=U, items=I, edges=E, nnz_sym=nnz, d=d, layers=L, hub_rows=graph.n_hub,
                             hub_chunks=graph.n_hub_chunks, l2="inputs (2.7 GB table, 0.8 GB indices) exceed L2", scale=args.scale),
-                roofline=dict(kernel="spmm_rows_kernel<16,1> (+hub kernels)", bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"],
+                roofline=dict(kernel="spmm_rows_kernel<16,1,64,20> (+hub kernels)", bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"],
                               unit="GB/s", frac=achieved / peaks["hbm_gbs"],
                               # ncu dram bytes per layer at this workload (profiles/): rows kernel 21.7 GB read + 5.4 GB
                               # written, hub-chunk kernel 17.6 GB read -> 44.7 GB against 52.9 GB algorithmic (L2 absorbs
@@ -432,7 +432,7 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
     return dict(metric="GCN propagate edges/s", value=nnz * L / t, unit="edges/s", ms_per_step=t * 1e3,
                 config=dict(workload="3-layer propagation, rows dealt round-robin over ranks, one NCCL all-gather per layer",
                             users=U, items=I, edges=E, nnz_sym=nnz, d=d, layers=L, world=world, scale=args.scale),
-                roofline=dict(kernel="spmm_rows_kernel<16,1> (+hub kernels)", bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"],
+                roofline=dict(kernel="spmm_rows_kernel<16,1,64,20> (+hub kernels)", bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"],
                               unit="GB/s per GPU", frac=achieved / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"]),
                 gpu_launches=None)
 
@@ -521,7 +521,7 @@ def run_train_leg(args, dev, rank, world, peaks):
     try:
         # fresh leaves: the eager steps above tied uw/iw's gradient accumulators to the default stream
         guw, giw = uw.detach().clone().requires_grad_(True), iw.detach().clone().requires_grad_(True)
-        gopt = torch.optim.Adam([guw, giw], lr=1e-3, capturable=True)
+        gopt = torch.optim.Adam([guw, giw], lr=1e-3, capturable=True, fused=True)
         gstep = cb.GraphedLightGCNStep(guw, giw, ei, L, cfg["reg"], B, gopt)
         for i in range(3):
             gstep(users[i], pos[i], neg[i])

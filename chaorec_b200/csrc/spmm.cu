@@ -14,6 +14,7 @@
 //   * hub rows (Zipf item rows with 10^3..10^6 neighbours) are cut into fixed chunks, each
 //     reduced by a whole CTA through shared memory into a partial row, then summed in chunk
 //     order -> deterministic, no atomics, no serial tail.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace chaorec {
@@ -186,9 +187,9 @@ __device__ __forceinline__ void row_epilogue(const SpmmArgs &a, int64_t r, int g
     }
 }
 
-template <int LANES, int NV>
+template <int LANES, int NV, int TPB = kThreads, bool WIDE = false>
 __device__ __forceinline__ void rows_body(const SpmmArgs &a, int64_t block) {
-    constexpr int kGroups = kThreads / LANES;
+    constexpr int kGroups = TPB / LANES;
     const int lane = threadIdx.x & 31;
     const int gl = threadIdx.x % LANES;
     const int64_t r = block * kGroups + threadIdx.x / LANES;
@@ -199,13 +200,14 @@ __device__ __forceinline__ void rows_body(const SpmmArgs &a, int64_t block) {
     float4 acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    gather_edges<LANES, NV, false>(a, e_lo, e_hi, gl, mask, acc);
+    gather_edges<LANES, NV, WIDE>(a, e_lo, e_hi, gl, mask, acc);
     row_epilogue<LANES, NV>(a, r, gl, acc);
 }
 
-template <int LANES, int NV>
-__global__ void __launch_bounds__(kThreads) spmm_rows_kernel(const SpmmArgs a) {
-    rows_body<LANES, NV>(a, blockIdx.x);
+// CTA size and register cap (minimum resident CTAs) are parameters: see launch_spmm.
+template <int LANES, int NV, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) spmm_rows_kernel(const SpmmArgs a) {
+    rows_body<LANES, NV, TPB>(a, blockIdx.x);
 }
 
 // Short rows (a user's ~12 items) are latency-bound when a sub-warp walks them one at a time:
@@ -546,7 +548,18 @@ int launch_spmm(const SpmmArgs &a, const HotArgs &h, int64_t n_hub_chunks, cudaS
         spmm_fused_kernel<LANES, NV><<<static_cast<unsigned>(blocks + n_hub_chunks), kThreads, 0, st>>>(a);
         return launch_status();
     } else {
-        if (blocks > 0) spmm_rows_kernel<LANES, NV><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(a);
+        // Four rows per CTA: a CTA keeps its slots until its longest row is done, so small CTAs waste fewer
+        // warp slots on the degree spread inside a block (measured at the 100M-edge config: 15.4 -> 18.1 G
+        // edges/s against 256-thread CTAs; 8 gathers in flight or a 32/40-register cap add nothing).
+        if constexpr (NV == 1) {
+            constexpr int TPB = 4 * LANES, MINB = (LANES >= 32) ? 10 : 20;
+            constexpr int G = TPB / LANES;
+            const int64_t nb = (a.M + G - 1) / G;
+            if (nb > 0x7fffffffLL) return CHAOREC_E_UNSUPPORTED;
+            if (nb > 0) spmm_rows_kernel<LANES, NV, TPB, MINB><<<static_cast<unsigned>(nb), TPB, 0, st>>>(a);
+        } else {
+            if (blocks > 0) spmm_rows_kernel<LANES, NV, kThreads, 1><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(a);
+        }
     }
     if (a.hub_rows != nullptr && a.n_hub > 0 && n_hub_chunks > 0) {
         if (n_hub_chunks > 0x7fffffffLL) return CHAOREC_E_UNSUPPORTED;
@@ -582,8 +595,10 @@ extern "C" int chaorec_spmm_hub_plan(int64_t nnz, int32_t *threshold, int32_t *c
     // A sub-warp walks its row four gathers at a time (~0.15 us per edge when nothing else hides the
     // latency), so the longest sub-warp row sets the kernel's tail.  Keep that tail near 1/8 of the
     // bandwidth-bound kernel time (nnz / 16 G edges/s): threshold ~ nnz / 16384, a power of two in [64, 1024].
+    // Above 256 the spread of row lengths inside a CTA costs more than the extra hub chunks (measured at
+    // 100M edges: thresholds 128 / 256 / 1024 / 4096 -> 18.4 / 18.7 / 18.1 / 16.7 G edges/s).
     int t = 64;
-    while (t < kHubThreshold && static_cast<int64_t>(t) * 2 * 16384 <= nnz) t *= 2;
+    while (t < 256 && static_cast<int64_t>(t) * 2 * 16384 <= nnz) t *= 2;
     *threshold = t;
     *chunk = 4 * t;
     return CHAOREC_OK;

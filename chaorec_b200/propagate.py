@@ -61,6 +61,9 @@ class CSRGraph:
             _lib.check(lib.chaorec_spmm_hub_plan(self.nnz, C.byref(t), C.byref(c)), "chaorec_spmm_hub_plan")
             threshold = t.value if threshold is None else threshold
             chunk = c.value if chunk is None else chunk
+        if os.environ.get("CHAOREC_SPMM_HUB_THR"):      # experiment switch
+            threshold = int(os.environ["CHAOREC_SPMM_HUB_THR"])
+            chunk = 4 * threshold
         self.hub_threshold, self.hub_chunk = int(threshold), int(chunk)
         deg = self.rowptr[1:] - self.rowptr[:-1]
         hubs = torch.nonzero(deg > self.hub_threshold).flatten()

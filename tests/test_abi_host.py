@@ -38,7 +38,7 @@ def test_abi_version_and_error_strings():
     assert lib.chaorec_spmm_hub_chunk() >= lib.chaorec_spmm_hub_threshold() > 0
     import ctypes
     t, c = ctypes.c_int32(0), ctypes.c_int32(0)
-    for nnz, want in ((0, 64), (562_350, 64), (4_000_000, 128), (20_000_000, 1024), (200_000_000, 1024)):
+    for nnz, want in ((0, 64), (562_350, 64), (4_000_000, 128), (20_000_000, 256), (200_000_000, 256)):
         assert lib.chaorec_spmm_hub_plan(nnz, ctypes.byref(t), ctypes.byref(c)) == 0
         assert (t.value, c.value) == (want, 4 * want)
     assert lib.chaorec_spmm_hub_row_chunks(30_000, 256) == 59       # ceil(30000/64)=469 -> 512-edge chunks
