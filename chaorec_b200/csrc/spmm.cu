@@ -50,6 +50,7 @@ struct SpmmArgs {
     int hub_threshold;   // rows with more edges than this belong to the hub kernels
     int hub_chunk;       // minimum edges per hub chunk (see hub_chunk_edges)
     float4 *hub_partials;
+    const int32_t *row_order;   // nullable: sub-warp i takes row row_order[i] (rows sorted by length)
     int *hub_counters;   // non-null: single-launch mode, the last chunk CTA of a row finishes it
     int64_t n_hub_chunks;
     int64_t M;
@@ -192,8 +193,9 @@ __device__ __forceinline__ void rows_body(const SpmmArgs &a, int64_t block) {
     constexpr int kGroups = TPB / LANES;
     const int lane = threadIdx.x & 31;
     const int gl = threadIdx.x % LANES;
-    const int64_t r = block * kGroups + threadIdx.x / LANES;
+    int64_t r = block * kGroups + threadIdx.x / LANES;
     if (r >= a.M) return;
+    if (a.row_order != nullptr) r = __ldg(a.row_order + r);
     const unsigned mask = group_mask<LANES>(lane);
     const int64_t e_lo = __ldg(a.rowptr + r), e_hi = __ldg(a.rowptr + r + 1);
     if (a.hub_rows != nullptr && e_hi - e_lo > a.hub_threshold) return;  // taken by the hub kernels
@@ -624,8 +626,9 @@ extern "C" int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *co
                                         float *acc, float alpha, int32_t acc_mode, const int32_t *hub_rows,
                                         const int64_t *hub_chunk_ptr, int32_t n_hub, int64_t n_hub_chunks,
                                         int32_t hub_threshold, int32_t hub_chunk, float *hub_partials,
-                                        int32_t *hub_counters, const int32_t *hot_col_enc, const int32_t *hot_cols,
-                                        int32_t n_hot, int64_t M, int64_t N, int32_t d, void *stream) {
+                                        int32_t *hub_counters, const int32_t *row_order, const int32_t *hot_col_enc,
+                                        const int32_t *hot_cols, int32_t n_hot, int64_t M, int64_t N, int32_t d,
+                                        void *stream) {
     if (!rowptr || !x || M < 0 || N < 0 || d <= 0) return CHAOREC_E_BADARG;
     if (!y && !acc) return CHAOREC_E_BADARG;
     if (acc_mode != 0 && acc_mode != 1) return CHAOREC_E_BADARG;
@@ -646,6 +649,7 @@ extern "C" int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *co
     a.hub_rows = (hub_rows && n_hub > 0) ? hub_rows : nullptr;
     a.hub_chunk_ptr = hub_chunk_ptr; a.n_hub = a.hub_rows ? n_hub : 0;
     a.hub_partials = reinterpret_cast<float4 *>(hub_partials);
+    a.row_order = row_order;
     a.hub_counters = a.hub_rows ? hub_counters : nullptr;
     a.n_hub_chunks = a.hub_rows ? n_hub_chunks : 0;
     a.hub_threshold = hub_threshold > 0 ? hub_threshold : kHubThreshold;
@@ -670,8 +674,9 @@ extern "C" int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, c
                                     float *acc, float alpha, int32_t acc_mode, const int32_t *hub_rows,
                                     const int64_t *hub_chunk_ptr, int32_t n_hub, int64_t n_hub_chunks,
                                     int32_t hub_threshold, int32_t hub_chunk, float *hub_partials,
-                                    int32_t *hub_counters, int64_t M, int64_t N, int32_t d, void *stream) {
+                                    int32_t *hub_counters, const int32_t *row_order, int64_t M, int64_t N,
+                                    int32_t d, void *stream) {
     return chaorec_spmm_csr_hot_f32(rowptr, col, val, row_scale, col_scale, x, y, acc, alpha, acc_mode, hub_rows,
                                     hub_chunk_ptr, n_hub, n_hub_chunks, hub_threshold, hub_chunk, hub_partials,
-                                    hub_counters, nullptr, nullptr, 0, M, N, d, stream);
+                                    hub_counters, row_order, nullptr, nullptr, 0, M, N, d, stream);
 }

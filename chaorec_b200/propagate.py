@@ -37,6 +37,7 @@ class CSRGraph:
     hub_threshold: int = 0                     # 0 = library default
     hub_chunk: int = 0
     hub_counters: Optional[torch.Tensor] = None   # int32 [n_hub] (single-launch mode), kept zero by the kernel
+    row_order: Optional[torch.Tensor] = None      # int32 [M]: rows by decreasing length (large graphs)
     SINGLE_LAUNCH_MAX_NNZ = 1 << 24
     _partials: Dict[int, torch.Tensor] = field(default_factory=dict)
     _hot: Dict[int, Optional[Tuple[torch.Tensor, torch.Tensor]]] = field(default_factory=dict)
@@ -86,6 +87,13 @@ class CSRGraph:
                                  if self.nnz < self.SINGLE_LAUNCH_MAX_NNZ else None)
         else:
             self.hub_rows, self.hub_chunk_ptr, self.n_hub_chunks, self.hub_counters = None, None, 0, None
+        # Large graphs: hand rows to sub-warps in order of decreasing length, so that the two rows of a warp
+        # and the four of a CTA finish together (no idle half-warps, no slots held by one long row).
+        mode = os.environ.get("CHAOREC_SPMM_ROW_ORDER", "auto")
+        if mode == "1" or (mode == "auto" and self.nnz >= self.SINGLE_LAUNCH_MAX_NNZ):
+            self.row_order = torch.sort(deg, descending=True, stable=True)[1].to(torch.int32).contiguous()
+        else:
+            self.row_order = None
         self._partials.clear()
         return self
 
@@ -194,7 +202,7 @@ def _spmm_raw(g: CSRGraph, x: torch.Tensor, y: Optional[torch.Tensor], acc: Opti
             _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.val), _lib.ptr(g.row_scale), _lib.ptr(g.col_scale),
             _lib.ptr(x), _lib.ptr(y), _lib.ptr(acc), float(alpha), int(acc_mode), _lib.ptr(g.hub_rows),
             _lib.ptr(g.hub_chunk_ptr), g.n_hub, g.n_hub_chunks, g.hub_threshold, g.hub_chunk, _lib.ptr(g.partials(d)),
-            _lib.ptr(g.hub_counters),
+            _lib.ptr(g.hub_counters), _lib.ptr(g.row_order),
             _lib.ptr(hot[0]) if hot else None, _lib.ptr(hot[1]) if hot else None, int(hot[1].numel()) if hot else 0,
             g.M, g.N, d, _lib.stream_ptr(x.device))
     _lib.check(rc, "chaorec_spmm_csr_hot_f32")

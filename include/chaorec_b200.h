@@ -92,13 +92,17 @@ int64_t chaorec_spmm_hub_row_chunks(int64_t row_nnz, int32_t chunk);
  * grid and the CTA that completes a hub row's last chunk sums its partials (in chunk order: results do
  * not depend on scheduling).  Without it hub rows take two extra launches.  With hub_rows == NULL
  * every row takes the sub-warp path (correct, slow for very long rows).
+ * row_order (nullable, int32 [M], a permutation of the rows): the order in which sub-warps take rows.
+ * Sorting rows by length (longest first) puts rows of equal length in the same warp and CTA, which
+ * removes the idle lanes and slots a mixed block leaves; results do not depend on it.
  * d must be a multiple of 4 and <= 512; x, y, acc 16-byte aligned.
  */
 int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float *val, const float *row_scale,
                          const float *col_scale, const float *x, float *y, float *acc, float alpha,
                          int32_t acc_mode, const int32_t *hub_rows, const int64_t *hub_chunk_ptr,
                          int32_t n_hub, int64_t n_hub_chunks, int32_t hub_threshold, int32_t hub_chunk,
-                         float *hub_partials, int32_t *hub_counters, int64_t M, int64_t N, int32_t d, void *stream);
+                         float *hub_partials, int32_t *hub_counters, const int32_t *row_order, int64_t M, int64_t N,
+                         int32_t d, void *stream);
 
 /*
  * Same product with hot-column staging: hot_col_enc int32 [nnz] is `col` with the n_hot most
@@ -112,8 +116,9 @@ int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *col, const fl
                              const float *col_scale, const float *x, float *y, float *acc, float alpha,
                              int32_t acc_mode, const int32_t *hub_rows, const int64_t *hub_chunk_ptr,
                              int32_t n_hub, int64_t n_hub_chunks, int32_t hub_threshold, int32_t hub_chunk,
-                             float *hub_partials, int32_t *hub_counters, const int32_t *hot_col_enc,
-                             const int32_t *hot_cols, int32_t n_hot, int64_t M, int64_t N, int32_t d, void *stream);
+                             float *hub_partials, int32_t *hub_counters, const int32_t *row_order,
+                             const int32_t *hot_col_enc, const int32_t *hot_cols, int32_t n_hot, int64_t M, int64_t N,
+                             int32_t d, void *stream);
 
 /*
  * BPR step around the propagation (Model/LightGCN.py:97-135): for B triples (users[b], pos[b], neg[b]),
