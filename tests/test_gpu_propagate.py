@@ -135,6 +135,11 @@ def test_spmm_hub_rows_empty_rows_and_scales():
     assert torch.equal(again, got) and int(graph.hub_counters.abs().sum()) == 0
     graph.hub_counters = None
     assert torch.equal(cb.spmm(graph, x.to(dev())), got)
+    # rows handed out by decreasing length (what large graphs do): same per-row arithmetic, same bits
+    deg = graph.rowptr[1:] - graph.rowptr[:-1]
+    graph.row_order = torch.sort(deg, descending=True, stable=True)[1].to(torch.int32).contiguous()
+    assert torch.equal(cb.spmm(graph, x.to(dev())), got)
+    graph.row_order = None
     # the large-graph plan on the same matrix
     graph.plan_hubs(threshold=1024, chunk=4096)
     assert graph.n_hub == 3 and graph.n_hub_chunks == 8 + 1 + 2
