@@ -182,6 +182,25 @@ def probe_fp32_peak(dev):
     return best
 
 
+def probe_tmem_read(dev, warps=16):
+    """TB/s at which `warps` warps per SM read fp32 accumulators out of tensor memory (nothing else running)."""
+    from chaorec_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    sink = torch.zeros(4, dtype=torch.int32, device=dev)
+    nbytes = C.c_double(0.0)
+    best = 0.0
+    for it in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.chaorec_probe_tmem_read(4000, warps, _lib.ptr(sink), C.byref(nbytes), _lib.stream_ptr(dev)), "probe")
+        e1.record()
+        torch.cuda.synchronize()
+        if it:
+            best = max(best, nbytes.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
 def run_eval_leg(args, dev, rank, world, peaks):
     import torch.distributed as dist
     import chaorec_b200 as cb

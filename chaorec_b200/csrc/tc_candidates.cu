@@ -82,6 +82,8 @@ struct TcArgs {
     uint64_t *cand_ws;        // [gridDim.x][BM][CH][TC_CAP]
     uint64_t *cand_out;       // [Ma][n_slices*CH][KP] approximate keys, best first (0 = empty)
     float *tprime_out;        // [Ma][n_slices*CH] approx score of the KP-th kept candidate (-inf: list complete)
+    const float *tau0;        // nullable [Ma][tau0_lists]: starting thresholds from the sample pre-pass (min over lists)
+    int tau0_lists;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -555,7 +557,16 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             // a row whose kept set could not leave room for a tile of appends (a user with hundreds of
             // train items) is not pre-filtered at all: it goes to the exact engine
             bool give_up = row_ok && ((r_keep + 32 > kTcTrigger) || (a.debug_mode & 3) != 0);
-            float tau = (row_ok && !give_up) ? -INFINITY : INFINITY;
+            // Starting threshold: -inf, or the row's threshold from the sample pre-pass (any value is safe --
+            // "every unlisted column scored <= the threshold in force when it was seen" holds either way,
+            // and a row that ends with too few candidates above it simply fails certification).
+            float tau_start = -INFINITY;
+            const bool seeded = a.tau0 != nullptr;
+            if (seeded && row_ok) {
+                tau_start = a.tau0[row * a.tau0_lists];
+                for (int l = 1; l < a.tau0_lists; ++l) tau_start = fminf(tau_start, a.tau0[row * a.tau0_lists + l]);
+            }
+            float tau = (row_ok && !give_up) ? tau_start : INFINITY;
             int cnt = 0;
             uint64_t *wr = row_buf;
             for (int t = t_lo; t < t_hi; ++t) {
@@ -598,7 +609,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 // 128, ... of the unit (the threshold then rises fast enough that a list never fills in
                 // between on ordinary data); a list that does get close to full compacts at once.
                 const int lt = t - t_lo;
-                const bool burst = lt >= 2 && (lt & (lt - 1)) == 0 && ((__ffs(lt) - 1) & 1);
+                const bool burst = !seeded && lt >= 2 && (lt & (lt - 1)) == 0 && ((__ffs(lt) - 1) & 1);
                 __syncwarp();                                     // appended keys visible to the whole warp
                 unsigned need = __ballot_sync(0xffffffffu, cnt > kTcTrigger || (burst && cnt > r_keep + 32));
                 while (need) {
@@ -633,7 +644,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int64_t row_src = row - lane + src;
                 if (row_src >= a.Ma) continue;                    // warp-uniform
                 const int list_id = sl * CH + ch;
-                uint64_t *out = a.cand_out + (static_cast<size_t>(row_src) * n_lists + list_id) * KP;
+                uint64_t *out = a.cand_out ? a.cand_out + (static_cast<size_t>(row_src) * n_lists + list_id) * KP : nullptr;
                 float tp = INFINITY;                              // +inf: cannot be certified -> exact engine
                 int nc = 0;
                 if (!gu_src && n_src <= TC_CAP) {
@@ -649,7 +660,8 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         tc_finish(s_args, row_src, buf_src, n_src, scratch, lane, KP, tau_src, nc, tp);
                     }
                 }
-                for (int t2 = lane; t2 < KP; t2 += 32) out[t2] = (t2 < nc) ? scratch[t2] : 0ull;
+                if (out != nullptr)
+                    for (int t2 = lane; t2 < KP; t2 += 32) out[t2] = (t2 < nc) ? scratch[t2] : 0ull;
                 if (lane == 0) a.tprime_out[static_cast<size_t>(row_src) * n_lists + list_id] = tp;
                 __syncwarp();
             }
@@ -686,6 +698,16 @@ __global__ void to_bf16_kernel(const float *__restrict__ x, int64_t n_rows, int 
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     // rounded up (fp32 summation error <= D*2^-24 relative): the norm feeds an upper bound
     if (lane == 0 && row_norm) row_norm[row] = sqrtf(ss) * (1.0f + 2.0e-7f * static_cast<float>(D));
+}
+
+// Sample pre-pass operand: every `stride`-th row of the bf16 B copy (evenly spaced = stratified over the id range).
+__global__ void gather_rows_bf16_kernel(const __nv_bfloat16 *__restrict__ src, int64_t stride, int64_t offset, int m, int D,
+                                        __nv_bfloat16 *__restrict__ dst) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // one 16-byte piece per thread
+    const int per_row = D / 8;
+    if (i >= static_cast<int64_t>(m) * per_row) return;
+    const int64_t j = i / per_row, c = i % per_row;
+    reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src + (j * stride + offset) * D)[c];
 }
 
 __global__ void max_reduce_kernel(const float *__restrict__ x, int64_t n, float *__restrict__ out) {
@@ -881,7 +903,20 @@ size_t al256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
 // -------------------------------------------------------------------------------------------------
 // Host orchestration shared by the eval and kNN entry points.
 // -------------------------------------------------------------------------------------------------
+constexpr int kSeedSampleMax = 16384;    // columns scored by the sample pre-pass
+constexpr int64_t kSeedMinCols = 65536;  // below this the main pass is short enough to warm up by itself
+
 struct HostShape { int BM, BN, CH; };
+
+// Smallest k with P(Poisson(x) >= k) <= p: the k-th best of an m-column sample sits, in expectation, at
+// rank k*Nb/m of the full row; the number of full-row columns above it is >= r unless a Poisson(x =
+// r*m/Nb) variable reaches k.
+static int seed_rank(double x, double p) {
+    double term = exp(-x), cdf = term;      // P(Poisson <= 0)
+    int k = 1;
+    while (1.0 - cdf > p && k < 64) { term *= x / k; cdf += term; ++k; }
+    return k;
+}
 static HostShape host_shape(int D) {
     return D <= BK ? HostShape{Shape<true>::BM, Shape<true>::BN, Shape<true>::CH}
                    : HostShape{Shape<false>::BM, Shape<false>::BN, Shape<false>::CH};
@@ -918,6 +953,8 @@ size_t tc_workspace_bytes(int64_t Ma, int64_t Nb, int D) {
     n += al256(static_cast<size_t>(Ma) * slices * hs.CH * 4);                   // t'
     n += al256(static_cast<size_t>(Ma) * 4);                            // fallback row list
     n += al256(static_cast<size_t>(Ma) * 8);                            // ... and their seed keys
+    n += al256(static_cast<size_t>(kSeedSampleMax) * D * 2);            // sample pre-pass: B sample (bf16)
+    n += al256(static_cast<size_t>(Ma) * hs.CH * 4);                    // ... and the starting thresholds
     n += rank_listed_workspace_bytes(D);                                // exact engine for uncertified rows
     return n;
 }
@@ -953,6 +990,8 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     float *tprime = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * hs.CH * 4);
     int32_t *fb_rows = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
     uint64_t *fb_seeds = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 8);
+    __nv_bfloat16 *bs16 = reinterpret_cast<__nv_bfloat16 *>(ws); ws += al256(static_cast<size_t>(kSeedSampleMax) * e.d * 2);
+    float *tau0 = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * hs.CH * 4);
     void *rank_ws = ws;
     const size_t rank_ws_bytes = workspace_bytes - static_cast<size_t>(ws - static_cast<unsigned char *>(workspace));
 
@@ -979,6 +1018,44 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     const int n_units = t.n_row_tiles * slices;
     const int grid = n_units < sm_count() ? n_units : sm_count();
     cudaError_t ce;
+    // ---- sample pre-pass: starting thresholds ----------------------------------------------------------
+    // A row's list normally warms up from -inf: ~r*ln(Nb/r) appends and a handful of compactions per row.
+    // Scoring an evenly spaced sample of m columns first (m/Nb of the work) gives every row a threshold
+    // near its (k*Nb/m)-th best score, so the main pass appends little more than that many entries and
+    // rarely compacts.  k is the smallest rank that leaves >= r columns above the threshold with
+    // probability 1 - 1e-3 (rows that end short fail certification and go to the exact engine).
+    int seed_m = kSeedSampleMax;
+    if (const char *env = getenv("CHAOREC_TC_SEED")) seed_m = atoi(env);
+    if (seed_m > kSeedSampleMax) seed_m = kSeedSampleMax;
+    seed_m = seed_m / 1024 * 1024;
+    if (seed_m > 0 && e.Nb >= kSeedMinCols) {
+        const int64_t stride = e.Nb / seed_m;
+        const int64_t pieces = static_cast<int64_t>(seed_m) * (e.d / 8);
+        gather_rows_bf16_kernel<<<static_cast<unsigned>((pieces + 255) / 256), 256, 0, stm>>>(b16, stride, stride / 2, seed_m, e.d, bs16);
+        CUtensorMap map_bs;
+        if (!make_map(&map_bs, bs16, seed_m, e.d, hs.BN)) return CHAOREC_E_LAUNCH;
+        const double r_typ = kp + 24.0;      // K' + self + a typical train-item list
+        int k_seed = seed_rank(r_typ * seed_m / static_cast<double>(e.Nb), 1e-3);
+        k_seed = (k_seed + hs.CH - 1) / hs.CH;                 // per list when a row has CH lists
+        if (k_seed < 4) k_seed = 4;
+        TcArgs p = t;
+        p.Nb = seed_m; p.n_slices = 1; p.tiles_per_slice = (seed_m + hs.BN - 1) / hs.BN;
+        p.mask_rowptr = nullptr; p.mask_col = nullptr; p.exclude_self = 0;
+        p.kp = k_seed; p.cand_out = nullptr; p.tprime_out = tau0; p.tau0 = nullptr; p.debug_mode = 0;
+        const int pgrid = p.n_row_tiles < sm_count() ? p.n_row_tiles : sm_count();
+        if (e.d <= BK) {
+            const size_t smem = tc_smem_bytes<true>();
+            ce = cudaFuncSetAttribute(tc_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (ce != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
+            tc_candidates_kernel<true><<<pgrid, kTcThreads, smem, stm>>>(map_a, map_bs, p);
+        } else {
+            const size_t smem = tc_smem_bytes<false>();
+            ce = cudaFuncSetAttribute(tc_candidates_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (ce != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
+            tc_candidates_kernel<false><<<pgrid, kTcThreads, smem, stm>>>(map_a, map_bs, p);
+        }
+        t.tau0 = tau0; t.tau0_lists = hs.CH;
+    }
     if (e.d <= BK) {
         const size_t smem = tc_smem_bytes<true>();
         ce = cudaFuncSetAttribute(tc_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -1021,4 +1098,45 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     return rank_launch_engine(fb, rank_ws, rank_ws_bytes, stm);
 }
 
+
+// Roofline probe: how fast can 32-bit accumulators be read out of tensor memory?  `warps` epilogue-style warps
+// per CTA (one CTA per SM) read all 512 columns of their lane quarter with tcgen05.ld.32x32b.x32, nothing else.
+__global__ void __launch_bounds__(512, 1) tmem_read_probe_kernel(int64_t iters, int warps, uint32_t *sink) {
+    __shared__ uint32_t tmem_base_s;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t base = tmem_base_s;
+    uint32_t x = 0;
+    if (warp < warps) {
+        const uint32_t lane_base = base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        const uint32_t col0 = static_cast<uint32_t>(warp >> 2) * 128u;     // 4 warps per lane quarter share the columns
+        for (int64_t it = 0; it < iters; ++it) {
+            uint32_t v[32], w[32];
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 64) {
+                tmem_ld32(lane_base + ((col0 + c) & 511u), v);
+                tmem_ld32(lane_base + ((col0 + c + 32) & 511u), w);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x ^= v[j] ^ w[j];
+            }
+        }
+    }
+    if (x == 0x12345678u && iters < 0) sink[0] = x;   // never true; keeps the loads alive
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(base, 512);
+}
+
 }  // namespace chaorec
+
+extern "C" int chaorec_probe_tmem_read(int64_t iters, int32_t warps, uint32_t *sink, double *bytes_out, void *stream) {
+    if (!sink || iters < 0 || warps < 1 || warps > 16) return CHAOREC_E_BADARG;
+    const int grid = chaorec::sm_count();
+    chaorec::tmem_read_probe_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(iters, warps, sink);
+    if (bytes_out) *bytes_out = static_cast<double>(iters) * warps * 32.0 * 128.0 * 4.0 * grid;
+    return chaorec::launch_status();
+}

@@ -217,6 +217,11 @@ int chaorec_knn_cosine_topk(const float *feats, int64_t N, int32_t D, int32_t k,
  * floating-point operations issued to *flops_out (host pointer).  Time it with CUDA events. */
 int chaorec_probe_fp32_fma(int64_t iters, float *sink, double *flops_out, void *stream);
 
+/* Reads 32-bit accumulators out of tensor memory with `warps` (1..16) warps per SM and nothing else
+ * (tcgen05.ld.32x32b.x32); writes the bytes read to *bytes_out.  The tensor engine's epilogue has to
+ * look at every fp32 score once, so this rate bounds rows*cols*4 bytes per pass whatever d is. */
+int chaorec_probe_tmem_read(int64_t iters, int32_t warps, uint32_t *sink, double *bytes_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -197,6 +197,25 @@ def test_million_user_config_sampled_bit_exact(canon):
     assert np.array_equal(sc[sample.to(dev())].cpu().numpy().view(np.uint32), csc.view(np.uint32))
 
 
+@pytest.mark.parametrize("K", [20, 50])
+def test_sample_prepass_thresholds_bit_exact(canon, K):
+    """Item tables of 65536+ rows start every row's threshold from a sample pre-pass (tc_candidates.cu):
+    all rows must still match the oracle bit for bit, and only a few may need the exact engine."""
+    U, I, d = 2500, 70_000, 64
+    u = ref_ops.normal_embeddings(U, d, 91)
+    it = ref_ops.normal_embeddings(I, d, 92)
+    tu, ti = ref_ops.synth_interactions(U, I, 12 * U, 93)
+    mask = cb.mask_csr_from_edges(tu.to(dev()), ti.to(dev()), U, I)
+    st = {}
+    idx, sc = cb.rank_topk(u.to(dev()), it.to(dev()), mask, K, 1e-6, id_offset=U, return_scores=True, stats=st)
+    rp, col = _csr_np(mask)
+    cidx, csc = canon.score_mask_topk(u.numpy(), it.numpy(), rp, col, 1e-6, K, id_offset=U)
+    assert np.array_equal(idx.cpu().numpy(), cidx)
+    assert np.array_equal(sc.cpu().numpy().view(np.uint32), csc.view(np.uint32))
+    if st["engine"] == "tensor":
+        assert st["fallback_rows"] <= U // 20
+
+
 def test_tensor_engine_is_used_and_rarely_falls_back(canon, engine):
     """The tcgen05 pre-filter must actually run for the big shapes, certify almost every row, and
     hand the rest to the exact engine (results are bit-exact either way)."""
