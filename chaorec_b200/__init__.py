@@ -9,7 +9,7 @@ from .propagate import (CSRGraph, LightGCNConv, bipartite_graph, csr_from_coo, c
                         graph_from_edge_index, lightgcn_forward, propagate_mean, resample_masked_graph, spmm)
 from .ranking import (MaskCSR, PositivesCSR, build_mask_csr, build_positives_csr, evaluate, evaluate_full,
                       gene_ranklist, hit_masks, mask_csr_from_edges, metrics_from_hits, rank_topk)
-from .train import GraphedLightGCNStep, bpr_loss, lightgcn_loss
+from .train import GraphedLightGCNStep, bpr_loss, lightgcn_loss, sample_negatives, training_batches
 from .knn import (build_knn_neighbourhood, get_knn_adj_mat, knn_laplacian_ones, knn_self_excluded,
                   knn_sym_laplacian, knn_topk, l2_normalize)
 
@@ -18,7 +18,7 @@ __all__ = [
     "lightgcn_forward", "propagate_mean", "spmm",
     "MaskCSR", "PositivesCSR", "build_mask_csr", "build_positives_csr", "evaluate", "evaluate_full",
     "gene_ranklist", "hit_masks", "mask_csr_from_edges", "metrics_from_hits", "rank_topk",
-    "GraphedLightGCNStep", "bpr_loss", "lightgcn_loss",
+    "GraphedLightGCNStep", "bpr_loss", "lightgcn_loss", "sample_negatives", "training_batches",
     "build_knn_neighbourhood", "get_knn_adj_mat", "knn_laplacian_ones", "knn_self_excluded",
     "knn_sym_laplacian", "knn_topk", "l2_normalize",
 ]

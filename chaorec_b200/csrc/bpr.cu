@@ -61,6 +61,44 @@ __global__ void __launch_bounds__(256) bpr_loss_grad_kernel(const float *__restr
     }
 }
 
+// Uniform negative sampling with train-set rejection (dataload.py:74-79): for draw i (global draw index
+// draw0 + i) candidates c_0, c_1, ... come from a counter-based generator -- splitmix64 of
+// (seed, draw index, attempt), mapped to [0, num_item) by a 64x64 -> high-64 multiply -- and the first one
+// that is not in the user's sorted train row is taken.  Stateless, so any batch of any epoch can be
+// regenerated, and oracle/ref_ops.py:sample_negatives reproduces it bit for bit.
+__device__ __host__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+constexpr int kMaxNegAttempts = 256;
+
+__global__ void __launch_bounds__(256) sample_negatives_kernel(const int64_t *__restrict__ users, int64_t n,
+                                                               const int64_t *__restrict__ rowptr,
+                                                               const int32_t *__restrict__ col, int64_t num_item,
+                                                               int64_t item_offset, uint64_t seed, uint64_t draw0,
+                                                               int64_t *__restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t u = users[i];
+    const int64_t lo0 = rowptr[u], hi0 = rowptr[u + 1];
+    const uint64_t base = splitmix64(seed ^ splitmix64(draw0 + static_cast<uint64_t>(i)));
+    int64_t c = 0;
+    for (int attempt = 0; attempt < kMaxNegAttempts; ++attempt) {
+        const uint64_t r = splitmix64(base + static_cast<uint64_t>(attempt));
+        c = static_cast<int64_t>(__umul64hi(r, static_cast<uint64_t>(num_item)));
+        int64_t lo = lo0, hi = hi0;                     // first entry >= c
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (col[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        if (lo == hi0 || col[lo] != c) break;           // not a train item of this user
+    }
+    out[i] = item_offset + c;
+}
+
 }  // namespace
 }  // namespace chaorec
 
@@ -77,5 +115,15 @@ extern "C" int chaorec_bpr_loss_grad_f32(const float *emb, const int64_t *users,
     if (d == 32) bpr_loss_grad_kernel<1><<<blocks, 256, 0, st>>>(emb, users, pos_items, neg_items, B, item_offset, reg_weight, loss_terms, grad);
     else if (d == 64) bpr_loss_grad_kernel<2><<<blocks, 256, 0, st>>>(emb, users, pos_items, neg_items, B, item_offset, reg_weight, loss_terms, grad);
     else bpr_loss_grad_kernel<4><<<blocks, 256, 0, st>>>(emb, users, pos_items, neg_items, B, item_offset, reg_weight, loss_terms, grad);
+    return launch_status();
+}
+
+extern "C" int chaorec_sample_negatives(const int64_t *users, int64_t n, const int64_t *mask_rowptr,
+                                        const int32_t *mask_col, int64_t num_item, int64_t item_offset, uint64_t seed,
+                                        uint64_t first_draw, int64_t *out, void *stream) {
+    if (!users || !mask_rowptr || !out || n < 0 || num_item <= 0) return CHAOREC_E_BADARG;
+    if (n == 0) return CHAOREC_OK;
+    sample_negatives_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        users, n, mask_rowptr, mask_col, num_item, item_offset, seed, first_draw, out);
     return launch_status();
 }

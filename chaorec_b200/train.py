@@ -59,6 +59,47 @@ def lightgcn_loss(user_weight: torch.Tensor, item_weight: torch.Tensor, edge_ind
     return loss, emb
 
 
+def sample_negatives(users: torch.Tensor, train_items, num_item: int, seed: int, first_draw: int = 0,
+                     item_offset: int = 0) -> torch.Tensor:
+    """Negative items for ``users`` (int64, on the GPU), one each, drawn uniformly from the items the user
+    has NOT interacted with -- the rejection loop of ``TrainingDataset.__getitem__`` (dataload.py:74-79) for
+    a whole batch in one launch.  ``train_items`` is the ``MaskCSR`` of ``user_item_dict`` (the evaluation
+    mask).  Returns ``item_offset + local id`` (pass ``num_user`` for the reference's global ids).  Draw i
+    depends only on ``(seed, first_draw + i)``: use ``first_draw = epoch * len(dataset) + batch_start``
+    to give every edge of every epoch its own draw.  (Same distribution as the reference; the reference's
+    ``random.sample`` stream itself is host state and is not reproduced.)"""
+    _lib.require_cuda(users, "users")
+    lib = _lib.load()
+    users = users.to(torch.int64).contiguous()
+    out = torch.empty_like(users)
+    with torch.cuda.device(users.device):
+        rc = lib.chaorec_sample_negatives(_lib.ptr(users), int(users.numel()), _lib.ptr(train_items.rowptr),
+                                          _lib.ptr(train_items.col), int(num_item), int(item_offset),
+                                          int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_draw) & 0xFFFFFFFFFFFFFFFF,
+                                          _lib.ptr(out), _lib.stream_ptr(users.device))
+    _lib.check(rc, "chaorec_sample_negatives")
+    return out
+
+
+def training_batches(edge_users: torch.Tensor, edge_pos_items: torch.Tensor, train_items, num_user: int,
+                     num_item: int, batch_size: int, epoch: int, seed: int = 0):
+    """One epoch of ``DataLoader(TrainingDataset(...), batch_size, shuffle=True)`` (dataload.py:60-106,
+    main.py's loader) without leaving the GPU: yields ``(users, pos_items, neg_items)`` int64 device tensors,
+    items as GLOBAL ids like the reference's triples.  ``edge_users`` / ``edge_pos_items`` are the training
+    pairs (global item ids) on the device.  The permutation comes from a device generator seeded with
+    ``(seed, epoch)``; negatives from :func:`sample_negatives`."""
+    n = int(edge_users.numel())
+    gen = torch.Generator(device=edge_users.device)
+    gen.manual_seed((int(seed) * 1000003 + int(epoch)) & 0x7FFFFFFFFFFFFFFF)
+    perm = torch.randperm(n, device=edge_users.device, generator=gen)
+    users_all = edge_users[perm].to(torch.int64)
+    pos_all = edge_pos_items[perm].to(torch.int64)
+    neg_all = sample_negatives(users_all, train_items, num_item, seed, first_draw=int(epoch) * n, item_offset=num_user)
+    for lo in range(0, n, batch_size):
+        hi = min(lo + batch_size, n)
+        yield users_all[lo:hi], pos_all[lo:hi], neg_all[lo:hi]
+
+
 class GraphedLightGCNStep:
     """One LightGCN BPR training step (forward, loss, backward, optimiser) captured in a CUDA graph.
 

@@ -209,6 +209,18 @@ int chaorec_knn_cosine_topk(const float *feats, int64_t N, int32_t D, int32_t k,
                             int64_t row_lo, int64_t row_hi, float *out_val, int64_t *out_idx, void *workspace,
                             size_t workspace_bytes, void *stream);
 
+/*
+ * Negative sampling of the training loader (dataload.py:74-79: draw items uniformly until one is not in
+ * user_item_dict[user]).  out[i] = item_offset + c, c the first candidate of draw (first_draw + i) that is
+ * not in row users[i] of the train-item CSR (mask_rowptr / mask_col, sorted local ids, the same arrays the
+ * evaluation mask uses).  Candidates are splitmix64(seed, draw index, attempt) mapped to [0, num_item) by a
+ * multiply-high, so draws are reproducible and independent of batch boundaries; after 256 rejected
+ * attempts (a user who interacted with nearly every item) the last candidate is returned.
+ */
+int chaorec_sample_negatives(const int64_t *users, int64_t n, const int64_t *mask_rowptr, const int32_t *mask_col,
+                             int64_t num_item, int64_t item_offset, uint64_t seed, uint64_t first_draw, int64_t *out,
+                             void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Roofline probes (used by bench.py to measure the denominators it reports against)
  * ---------------------------------------------------------------------------------------- */

@@ -363,3 +363,34 @@ def xavier_embeddings(n: int, d: int, seed: int) -> torch.Tensor:
 def normal_embeddings(n: int, d: int, seed: int, std: float = 0.1) -> torch.Tensor:
     g = torch.Generator().manual_seed(seed)
     return torch.randn(n, d, generator=g) * std
+
+
+# ---------------------------------------------------------------------------------------------
+# Negative sampling (dataload.py:74-79) with the counter-based generator of csrc/bpr.cu
+# ---------------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def sample_negatives(users, user_item_sets, num_item: int, seed: int, first_draw: int = 0, item_offset: int = 0):
+    """Restatement of ``TrainingDataset.__getitem__``'s rejection loop (dataload.py:74-79: draw uniformly
+    from all items until the draw is not in ``user_item_dict[user]``) with the stateless generator the CUDA
+    kernel uses, so both sides can be compared bit for bit.  ``user_item_sets[u]`` = set of LOCAL train item
+    ids of user u.  Pure Python: small cases only."""
+    out = []
+    for i, u in enumerate(users):
+        base = _splitmix64((seed & _M64) ^ _splitmix64((first_draw + i) & _M64))
+        c = 0
+        for attempt in range(256):
+            r = _splitmix64((base + attempt) & _M64)
+            c = (r * num_item) >> 64
+            if c not in user_item_sets[int(u)]:
+                break
+        out.append(item_offset + c)
+    return out

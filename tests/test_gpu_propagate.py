@@ -343,3 +343,38 @@ def test_cuda_graph_training_step_matches_eager():
         assert abs(float(gl) - want) <= 1e-5 * abs(want)
     torch.cuda.synchronize()
     assert rel_err(uw2, uw.detach().cpu()) <= 1e-5 and rel_err(iw2, iw.detach().cpu()) <= 1e-5
+
+
+def test_negative_sampler_bit_exact_vs_oracle():
+    U, I = 300, 97
+    tu, ti = ref_ops.synth_interactions(U, I, 6000, 31)
+    ti[tu == 5] = ti[tu == 5] % 3                       # a user with a tiny train set
+    mask = cb.mask_csr_from_edges(tu.to(dev()), ti.to(dev()), U, I)
+    sets = {u: set() for u in range(U)}
+    for u, i in zip(tu.tolist(), ti.tolist()):
+        sets[u].add(i)
+    users = torch.randint(0, U, (5000,), generator=torch.Generator().manual_seed(4))
+    got = cb.sample_negatives(users.to(dev()), mask, I, seed=12345, first_draw=777, item_offset=U)
+    want = ref_ops.sample_negatives(users.tolist(), sets, I, 12345, first_draw=777, item_offset=U)
+    assert got.cpu().tolist() == want
+    assert all((g - U) not in sets[u] for g, u in zip(got.cpu().tolist(), users.tolist()))
+    # batch boundaries do not matter
+    part = cb.sample_negatives(users[1000:2000].to(dev()), mask, I, seed=12345, first_draw=1777, item_offset=U)
+    assert torch.equal(part, got[1000:2000])
+
+
+def test_training_batches_cover_every_edge_once_with_valid_negatives():
+    U, I = 200, 150
+    tu, ti = ref_ops.synth_interactions(U, I, 3000, 33)
+    mask = cb.mask_csr_from_edges(tu.to(dev()), ti.to(dev()), U, I)
+    seen = []
+    for users, pos, neg in cb.training_batches(tu.to(dev()), (ti + U).to(dev()), mask, U, I, 256, epoch=3, seed=9):
+        assert users.shape == pos.shape == neg.shape and users.numel() <= 256
+        assert int(neg.min()) >= U and int(neg.max()) < U + I
+        seen.append(torch.stack((users, pos, neg), 1).cpu())
+    trip = torch.cat(seen)
+    assert sorted((trip[:, 0] * (U + I) + trip[:, 1]).tolist()) == sorted((tu * (U + I) + ti + U).tolist())
+    train = set((tu * I + ti).tolist())
+    assert all((int(u) * I + int(n) - U) not in train for u, n in zip(trip[:, 0], trip[:, 2]))
+    again = torch.cat([torch.stack(b, 1).cpu() for b in cb.training_batches(tu.to(dev()), (ti + U).to(dev()), mask, U, I, 256, epoch=3, seed=9)])
+    assert torch.equal(again, trip)
