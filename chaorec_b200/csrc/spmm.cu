@@ -573,6 +573,41 @@ int launch_spmm(const SpmmArgs &a, const HotArgs &h, int64_t n_hub_chunks, cudaS
     return launch_status();
 }
 
+// SDDMM on a CSR pattern: out[e] = <a[row(e), :], b[col[e], :]>.  The adjoint of the SpMM with respect to its
+// edge values (LATTICE / MICRO learn their item graph through them, Model/LATTICE.py:142-160), and the
+// cosine values of a kNN pattern.  One warp per row: the row of `a` stays in registers (d <= 512), every
+// edge gathers its row of `b`, the partial dot products are shuffle-reduced.
+__global__ void __launch_bounds__(256) sddmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                        const float4 *__restrict__ a, const float4 *__restrict__ b,
+                                                        float *__restrict__ out, int64_t M, int dq) {
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (r >= M) return;
+    const int lane = threadIdx.x & 31;
+    float4 av[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const int q = lane + 32 * v;
+        av[v] = q < dq ? __ldg(a + r * dq + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int64_t e_lo = __ldg(rowptr + r), e_hi = __ldg(rowptr + r + 1);
+    for (int64_t e = e_lo; e < e_hi; ++e) {
+        const int64_t c = __ldg(col + e);
+        float s = 0.0f;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int q = lane + 32 * v;
+            if (q < dq) {
+                const float4 bv = __ldg(b + c * dq + q);
+                s = fmaf(av[v].x, bv.x, s); s = fmaf(av[v].y, bv.y, s);
+                s = fmaf(av[v].z, bv.z, s); s = fmaf(av[v].w, bv.w, s);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) out[e] = s;
+    }
+}
+
 __global__ void degree_inv_sqrt_kernel(const int64_t *__restrict__ rowptr, int64_t M, float eps,
                                        float *__restrict__ out) {
     const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -679,4 +714,16 @@ extern "C" int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, c
     return chaorec_spmm_csr_hot_f32(rowptr, col, val, row_scale, col_scale, x, y, acc, alpha, acc_mode, hub_rows,
                                     hub_chunk_ptr, n_hub, n_hub_chunks, hub_threshold, hub_chunk, hub_partials,
                                     hub_counters, row_order, nullptr, nullptr, 0, M, N, d, stream);
+}
+
+extern "C" int chaorec_sddmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float *a, const float *b,
+                                     float *out, int64_t M, int32_t d, void *stream) {
+    if (!rowptr || !a || !b || M < 0 || d <= 0) return CHAOREC_E_BADARG;
+    if (d % 4 != 0 || d > 512) return CHAOREC_E_UNSUPPORTED;
+    if (!aligned16(a) || !aligned16(b)) return CHAOREC_E_ALIGN;
+    if (M == 0) return CHAOREC_OK;
+    if (!col || !out) return CHAOREC_E_BADARG;
+    sddmm_csr_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        rowptr, col, reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(b), out, M, d / 4);
+    return launch_status();
 }

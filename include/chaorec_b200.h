@@ -121,6 +121,16 @@ int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *col, const fl
                              int32_t d, void *stream);
 
 /*
+ * SDDMM on a CSR pattern: out[e] = <a[row(e),:], b[col[e],:]> for every stored edge e (fp32, d % 4 == 0,
+ * d <= 512; a is [M, d], b is [N, d]).  The gradient of chaorec_spmm_csr_f32 with respect to its edge values
+ * (a = dL/dy, b = x) -- the path through which LATTICE / MICRO learn their item-item graph
+ * (Model/LATTICE.py:142-160) -- and, with a = b = normalised features, the cosine values of a kNN pattern
+ * (build_sim + topk values, Model/LATTICE.py:45-52,67-74).
+ */
+int chaorec_sddmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float *a, const float *b, float *out,
+                          int64_t M, int32_t d, void *stream);
+
+/*
  * BPR step around the propagation (Model/LightGCN.py:97-135): for B triples (users[b], pos[b], neg[b]),
  * rows users[b], item_offset+pos[b], item_offset+neg[b] of emb [N, d]:
  *   loss = -mean log(sigmoid(<u,p> - <u,n>) + 1e-5) + reg_weight * (mean(u^2) + mean(p^2) + mean(n^2))

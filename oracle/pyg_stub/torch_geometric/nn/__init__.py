@@ -1,0 +1,1 @@
+from .conv import MessagePassing  # noqa: F401

@@ -394,3 +394,51 @@ def sample_negatives(users, user_item_sets, num_item: int, seed: int, first_draw
                 break
         out.append(item_offset + c)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# LATTICE learned item graph (Model/LATTICE.py:45-74,137-177), dense restatement
+# ---------------------------------------------------------------------------------------------
+def lattice_build_sim(context: torch.Tensor) -> torch.Tensor:
+    """Model/LATTICE.py:67-74."""
+    cn = context.div(torch.norm(context, p=2, dim=-1, keepdim=True))
+    return torch.mm(cn, cn.transpose(1, 0))
+
+
+def lattice_knn_neighbourhood(adj: torch.Tensor, topk: int) -> torch.Tensor:
+    """Model/LATTICE.py:45-52."""
+    knn_val, knn_ind = torch.topk(adj, topk, dim=-1)
+    return torch.zeros_like(adj).scatter_(-1, knn_ind, knn_val)
+
+
+def lattice_normalized_laplacian(adj: torch.Tensor) -> torch.Tensor:
+    """Model/LATTICE.py:56-64."""
+    d_inv_sqrt = torch.pow(torch.sum(adj, -1), -0.5)
+    d_inv_sqrt = torch.where(torch.isinf(d_inv_sqrt), torch.zeros_like(d_inv_sqrt), d_inv_sqrt)
+    return d_inv_sqrt.unsqueeze(1) * adj * d_inv_sqrt.unsqueeze(0)          # == diagflat(d) @ adj @ diagflat(d)
+
+
+def lattice_forward(p: dict, edge_index: torch.Tensor, num_user: int, num_item: int, topk: int, lambda_coeff: float,
+                    mm_layers: int, n_layers: int) -> torch.Tensor:
+    """``LATTICE.forward(build_item_graph=True)`` (Model/LATTICE.py:137-177) on plain tensors: ``p`` holds
+    user, item, image, text, image_w, image_b, text_w, text_b, modal.  Dense [N, N] like the reference."""
+    image_feats = p["image"] @ p["image_w"].t() + p["image_b"]
+    text_feats = p["text"] @ p["text_w"].t() + p["text_b"]
+    weight = torch.softmax(p["modal"], dim=0)
+    image_adj = lattice_knn_neighbourhood(lattice_build_sim(image_feats), topk)
+    text_adj = lattice_knn_neighbourhood(lattice_build_sim(text_feats), topk)
+    learned = lattice_normalized_laplacian(weight[0] * image_adj + weight[1] * text_adj)
+    io = lattice_normalized_laplacian(lattice_knn_neighbourhood(lattice_build_sim(p["image"].detach()), topk))
+    to = lattice_normalized_laplacian(lattice_knn_neighbourhood(lattice_build_sim(p["text"].detach()), topk))
+    item_adj = (1 - lambda_coeff) * learned + lambda_coeff * (weight[0] * io + weight[1] * to)
+    h = p["item"]
+    for _ in range(mm_layers):
+        h = torch.mm(item_adj, h)
+    ego = torch.cat((p["user"], p["item"]), dim=0)
+    embs = [ego]
+    for _ in range(n_layers):
+        ego = pyg_lightgcn_conv(ego, edge_index)                 # LATTICEGCNConv == LightGCNConv (Model/LATTICE.py:18-42)
+        embs.append(ego)
+    mean = torch.stack(embs, dim=1).mean(dim=1)
+    u_g, i_g = torch.split(mean, [num_user, num_item], dim=0)
+    return torch.cat((u_g, i_g + torch.nn.functional.normalize(h, p=2, dim=1)), dim=0)

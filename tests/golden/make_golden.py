@@ -21,6 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("CHAOREC_REFERENCE", "/root/reference")
 
+_ARGS = sys.argv[1:]
 sys.argv = ["make_golden"]          # arg_parser.parse_args() runs at import time
 sys.path.insert(0, os.path.join(ROOT, "oracle", "pyg_stub"))
 sys.path.insert(0, REF)
@@ -261,8 +262,44 @@ def real_graph_case():
                         result_absmax=np.abs(result.numpy()).max())
 
 
+def lattice_case():
+    """Model/LATTICE.py as is (through the PyG stand-in): forward(build_item_graph=True) and the gradients of
+    a fixed linear functional of the result with respect to every parameter the item graph touches."""
+    from Model.LATTICE import LATTICE
+    U, I, E, dv, dt, fe, dE, k = 120, 200, 1500, 48, 40, 32, 64, 10
+    torch.manual_seed(77)
+    tu, ti = ref_ops.synth_interactions(U, I, E, 771)
+    train = np.stack((tu.numpy(), ti.numpy() + U), 1)
+    uid = {u: set() for u in range(U)}
+    for u, i in train:
+        uid[int(u)].add(int(i))
+    g = torch.Generator().manual_seed(772)
+    v_feat = torch.randn(I, dv, generator=g)
+    t_feat = torch.randn(I, dt, generator=g)
+    model = LATTICE(U, I, train, uid, v_feat.clone(), t_feat.clone(), dE, fe, 1e-4, 2, 1, k, 'add', 0.9, torch.device('cpu'))
+    with torch.no_grad():
+        model.modal_weight.copy_(torch.tensor([0.3, 0.8]))
+    R = torch.randn(U + I, dE, generator=g)
+    params = dict(user=model.user_embedding.weight, item=model.item_embedding.weight, image=model.image_embedding.weight,
+                  text=model.text_embedding.weight, image_w=model.image_trs.weight, image_b=model.image_trs.bias,
+                  text_w=model.text_trs.weight, text_b=model.text_trs.bias, modal=model.modal_weight)
+    start = {n: p.detach().clone().numpy() for n, p in params.items()}
+    result = model.forward(build_item_graph=True)
+    (result * R).sum().backward()
+    out = dict(U=U, I=I, k=k, lambda_coeff=0.9, mm_layers=1, n_layers=2, train=train, R=R.numpy(), result=result.detach().numpy(),
+               item_adj=model.item_adj.detach().numpy(), image_original_adj=model.image_original_adj.numpy(),
+               text_original_adj=model.text_original_adj.numpy())
+    for n, p in params.items():
+        out["p_" + n] = start[n]
+        out["g_" + n] = p.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "lattice_small.npz"), **out)
+    print("lattice_small.npz", result.shape, float(result.abs().max()))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["lightgcn", "train", "freedom", "metrics", "real"]
+    which = _ARGS or ["lightgcn", "train", "freedom", "metrics", "real", "lattice"]
+    if "lattice" in which:
+        lattice_case()
     if "lightgcn" in which:
         lightgcn_case()
     if "train" in which:
