@@ -10,6 +10,7 @@ from .propagate import (CSRGraph, LightGCNConv, bipartite_graph, csr_from_coo, c
 from .ranking import (MaskCSR, PositivesCSR, build_mask_csr, build_positives_csr, evaluate, evaluate_full,
                       gene_ranklist, hit_masks, mask_csr_from_edges, metrics_from_hits, rank_topk)
 from .train import GraphedLightGCNStep, bpr_loss, lightgcn_loss, sample_negatives, training_batches
+from .cooccur import user_cooccurrence_topk, user_graph_dict
 from .item_graph import ItemGraph, KnnPattern, knn_graph, normalized_values, original_graph, pattern_matmul
 from .knn import (build_knn_neighbourhood, get_knn_adj_mat, knn_laplacian_ones, knn_self_excluded,
                   knn_sym_laplacian, knn_topk, l2_normalize)
@@ -22,5 +23,6 @@ __all__ = [
     "GraphedLightGCNStep", "bpr_loss", "lightgcn_loss", "sample_negatives", "training_batches",
     "build_knn_neighbourhood", "get_knn_adj_mat", "knn_laplacian_ones", "knn_self_excluded",
     "knn_sym_laplacian", "knn_topk", "l2_normalize",
+    "user_cooccurrence_topk", "user_graph_dict",
     "ItemGraph", "KnnPattern", "knn_graph", "normalized_values", "original_graph", "pattern_matmul",
 ]

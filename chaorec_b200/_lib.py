@@ -45,6 +45,8 @@ SIGNATURES = {
     "chaorec_l2_normalize_f32": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "chaorec_knn_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "chaorec_knn_cosine_topk": (C.c_int, [_p, _i64, _i32, _i32, C.c_int, _i64, _i64, _p, _p, _p, _sz, _p]),
+    "chaorec_cooccurrence_max_users": (_i64, []),
+    "chaorec_cooccurrence_topk": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _i64, _i64, _p, _p, _p, _p]),
     "chaorec_probe_fp32_fma": (C.c_int, [_i64, _p, _p, _p]),
     "chaorec_probe_tmem_read": (C.c_int, [_i64, _i32, _p, _p, _p]),
 }

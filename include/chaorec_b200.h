@@ -231,6 +231,20 @@ int chaorec_sample_negatives(const int64_t *users, int64_t n, const int64_t *mas
                              int64_t num_item, int64_t item_offset, uint64_t seed, uint64_t first_draw, int64_t *out,
                              void *stream);
 
+/*
+ * User-user co-occurrence graph (dualgnn-gen-u-u-matrix.py:20-50,85-103): for every user u in
+ * [row_lo, row_hi) the min(k, nnz) users v != u with the largest |items(u) & items(v)|, best first, ties in
+ * ascending v.  user_rowptr/user_items: the users' (deduplicated, sorted) local item lists as CSR -- the
+ * evaluation mask arrays; item_rowptr/item_users: the transpose (users of every item).  out_idx / out_cnt:
+ * int32 [U*k] (row u at u*k; unused slots -1 / 0), out_n int32 [U] = entries written for the row.
+ * k <= 256, U <= chaorec_cooccurrence_max_users() (the row's counters live in shared memory), every
+ * user with fewer than 65536 items.
+ */
+int64_t chaorec_cooccurrence_max_users(void);
+int chaorec_cooccurrence_topk(const int64_t *user_rowptr, const int32_t *user_items, const int64_t *item_rowptr,
+                              const int32_t *item_users, int64_t U, int64_t I, int32_t k, int64_t row_lo, int64_t row_hi,
+                              int32_t *out_idx, int32_t *out_cnt, int32_t *out_n, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Roofline probes (used by bench.py to measure the denominators it reports against)
  * ---------------------------------------------------------------------------------------- */

@@ -442,3 +442,31 @@ def lattice_forward(p: dict, edge_index: torch.Tensor, num_user: int, num_item: 
     mean = torch.stack(embs, dim=1).mean(dim=1)
     u_g, i_g = torch.split(mean, [num_user, num_item], dim=0)
     return torch.cat((u_g, i_g + torch.nn.functional.normalize(h, p=2, dim=1)), dim=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# User-user co-occurrence graph (dualgnn-gen-u-u-matrix.py:20-50,85-103)
+# ---------------------------------------------------------------------------------------------
+def user_cooccurrence_matrix(train_edges: np.ndarray, num_user: int) -> np.ndarray:
+    """``gen_user_matrix`` (dualgnn-gen-u-u-matrix.py:20-50): C[u][v] = |items(u) & items(v)| for u != v, 0 on the
+    diagonal, as R @ R.T of the deduplicated binary interaction matrix."""
+    e = np.unique(np.asarray(train_edges, dtype=np.int64), axis=0)
+    items, inv = np.unique(e[:, 1], return_inverse=True)
+    R = np.zeros((num_user, items.size), dtype=np.int64)
+    R[e[:, 0], inv] = 1
+    C = R @ R.T
+    np.fill_diagonal(C, 0)
+    return C
+
+
+def user_graph_topk(C: np.ndarray, k: int = 200):
+    """dualgnn-gen-u-u-matrix.py:85-103 under the canonical order (count descending, ties -> smaller user id;
+    ``torch.topk`` leaves the order among equal counts unspecified): {u: [indices, float values]}."""
+    out = {}
+    for u in range(C.shape[0]):
+        row = C[u]
+        nz = int((row > 0).sum())
+        kk = min(nz, k)
+        order = np.lexsort((np.arange(row.size), -row))[:kk]
+        out[u] = [order.tolist(), [float(row[v]) for v in order]]
+    return out

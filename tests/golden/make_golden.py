@@ -262,6 +262,29 @@ def real_graph_case():
                         result_absmax=np.abs(result.numpy()).max())
 
 
+def cooccurrence_case():
+    """dualgnn-gen-u-u-matrix.py run as is (gen_user_matrix + the top-200 loop body) on a small seeded graph."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("dualgnn_gen", os.path.join(REF, "dualgnn-gen-u-u-matrix.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    U, I, E = 150, 60, 1200
+    tu, ti = ref_ops.synth_interactions(U, I, E, 881)
+    train = np.stack((tu.numpy(), ti.numpy() + U), 1)
+    M = mod.gen_user_matrix(train, U)
+    k = 20                                     # the script's 200, scaled to the fixture (rows here have up to ~140 entries)
+    vals = np.zeros((U, k), dtype=np.float32)
+    n = np.zeros(U, dtype=np.int64)
+    for i in range(U):                         # dualgnn-gen-u-u-matrix.py:85-103 with 200 -> k
+        nz = len(torch.nonzero(M[i]))
+        kk = nz if nz <= k else k
+        top = torch.topk(M[i], int(kk))
+        vals[i, :kk] = top.values.numpy()
+        n[i] = kk
+    np.savez_compressed(os.path.join(HERE, "cooccurrence_small.npz"), U=U, I=I, k=k, train=train, matrix=M.numpy(), topk_values=vals, topk_n=n)
+    print("cooccurrence_small.npz", M.shape, float(M.max()))
+
+
 def lattice_case():
     """Model/LATTICE.py as is (through the PyG stand-in): forward(build_item_graph=True) and the gradients of
     a fixed linear functional of the result with respect to every parameter the item graph touches."""
@@ -297,9 +320,11 @@ def lattice_case():
 
 
 if __name__ == "__main__":
-    which = _ARGS or ["lightgcn", "train", "freedom", "metrics", "real", "lattice"]
+    which = _ARGS or ["lightgcn", "train", "freedom", "metrics", "real", "lattice", "cooccurrence"]
     if "lattice" in which:
         lattice_case()
+    if "cooccurrence" in which:
+        cooccurrence_case()
     if "lightgcn" in which:
         lightgcn_case()
     if "train" in which:

@@ -140,3 +140,25 @@ def test_lattice_item_graph_sparse_operator_matches_reference():
     # the detached operator (Model/LATTICE.py:161) gives the same product and carries no graph
     hd = graph.detach().mm(p["item"].detach())
     assert not hd.requires_grad and float((hd - graph.mm(p["item"]).detach()).abs().max()) == 0.0
+
+
+def test_user_cooccurrence_graph_matches_reference_and_oracle():
+    g = load_golden("cooccurrence_small.npz")
+    U, I, k = int(g["U"]), int(g["I"]), int(g["k"])
+    train = torch.from_numpy(g["train"])
+    idx, cnt, n = cb.user_cooccurrence_topk(train[:, 0].to(dev()), (train[:, 1] - U).to(dev()), U, I, k)
+    want = ref_ops.user_graph_topk(g["matrix"].astype(np.int64), k)
+    got = cb.user_graph_dict(idx, cnt, n)
+    assert got == want                                                      # ids and counts, canonical order
+    assert np.array_equal(n.cpu().numpy(), g["topk_n"])
+    for u in range(U):                                                      # the reference's own values
+        assert got[u][1] == g["topk_values"][u, :len(got[u][1])].tolist()
+    # a bigger seeded graph against the oracle, k = 200 like the script, and row sharding
+    U2, I2 = 3000, 800
+    tu, ti = ref_ops.synth_interactions(U2, I2, 30000, 882)
+    idx, cnt, n = cb.user_cooccurrence_topk(tu.to(dev()), ti.to(dev()), U2, I2, 200)
+    C = ref_ops.user_cooccurrence_matrix(np.stack((tu.numpy(), ti.numpy()), 1), U2)
+    assert cb.user_graph_dict(idx, cnt, n) == ref_ops.user_graph_topk(C, 200)
+    idx_b, cnt_b, n_b = cb.user_cooccurrence_topk(tu.to(dev()), ti.to(dev()), U2, I2, 200, row_range=(1000, 2000))
+    assert torch.equal(idx_b[1000:2000], idx[1000:2000]) and torch.equal(cnt_b[1000:2000], cnt[1000:2000])
+    assert int(n_b[:1000].sum()) == 0 and int(n_b[2000:].sum()) == 0
