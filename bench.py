@@ -293,9 +293,10 @@ def run_eval_leg(args, dev, rank, world, peaks):
         roof = dict(kernel="tc_candidates_kernel (tcgen05 bf16 pre-filter; time includes bf16 conversion, fp32 re-score + "
                            "certification and the exact fallback launch)", bound="tensor", achieved=achieved,
                     peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops"],
-                    # dram__bytes_read+write of tc_candidates_kernel<true> at this exact workload on 1 GPU, from the
-                    # ncu --set full capture summarised in profiles/ (3.5 GB read + 8.6 GB written, mostly list appends)
-                    traffic=(12.1e9 if (world == 1 and args.scale == 1.0) else None),
+                    # dram__bytes_read+write of the main tc_candidates_kernel<true> launch at this exact workload on 1 GPU,
+                    # from the ncu --set full capture profiles/r01_final_tc_eval_summary.csv (1.39 GB read + 1.65 GB written)
+                    traffic=(3.05e9 if (world == 1 and args.scale == 1.0) else None),
+                    tmem_read_tbps_measured=probe_tmem_read(dev),
                     peak_source=peaks["source"] + " (bf16 dense burst)", algorithmic_flops_per_launch=flops,
                     kernel_ms=t_rank_kernel * 1e3, fallback_rows=st.get("fallback_rows"),
                     fp32_fma_peak_tflops_measured=fp32_peak)
@@ -310,7 +311,7 @@ def run_eval_leg(args, dev, rank, world, peaks):
         e2e=dict(value=e2e_value, unit="users/s", h2d_bytes_per_step=batch.h2d_bytes(), d2h_bytes_per_step=n_local * 8,
                  includes="H2D of embeddings+mask+positives, rank kernel, hits kernel, D2H hit masks, gather, host fp64 metrics"),
         roofline=roof, engine=st.get("engine"),
-        gpu_launches=(7 if tensor else 2) * args.steps,
+        gpu_launches=(10 if tensor else 2) * args.steps,
         config=dict(workload="full-rank top-20 eval, 1M users x 200k items, d=64 (BASELINE configs[3])", users=U, items=I,
                     d=d, topk=K, mask_items_per_user=EVAL_CFG["mask_per_user"], sharding=f"users/{world}",
                     l2="flushed between steps (192 MiB write)", scale=args.scale),
@@ -400,10 +401,10 @@ def run_propagate_leg(args, dev, rank, world, peaks):
                             hub_chunks=graph.n_hub_chunks, l2="inputs (2.7 GB table, 0.8 GB indices) exceed L2", scale=args.scale),
                 roofline=dict(kernel="spmm_rows_kernel<16,1,64,20> (+hub kernels)", bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"],
                               unit="GB/s", frac=achieved / peaks["hbm_gbs"],
-                              # ncu dram bytes per layer at this workload (profiles/): rows kernel 21.7 GB read + 5.4 GB
-                              # written, hub-chunk kernel 17.6 GB read -> 44.7 GB against 52.9 GB algorithmic (L2 absorbs
-                              # the popular item rows)
-                              traffic=(44.7e9 if args.scale == 1.0 else None), peak_source=peaks["source"],
+                              # ncu dram bytes per layer at this workload (profiles/r01_final_spmm_*_summary.csv): rows
+                              # kernel 21.2 GB read + 5.3 GB written, hub-chunk kernel 20.6 GB read + 0.2 GB written
+                              # -> 47.3 GB against 52.9 GB algorithmic (L2 absorbs the popular item rows)
+                              traffic=(47.3e9 if args.scale == 1.0 else None), peak_source=peaks["source"],
                               algorithmic_bytes_per_layer=bytes_layer),
                 gpu_launches=(1 + (2 if graph.n_hub else 0)) * L * args.steps)
 

@@ -1,7 +1,23 @@
+#!/bin/bash
+# End-of-round evidence: launch list of the default bench command + ncu --set full captures of the dominant
+# kernels; raw/source pages are exported to CSV on the box (the .ncu-rep files themselves are dropped when large).
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-KREG='regex:rank_topk|spmm_|topk_hits|row_norm|row_scale|tc_cand|rescore|to_bf16|max_reduce|slice_merge|degree_inv'
-(timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -c 400 --csv --log-file gpurun_out/launches_r01_final.csv python bench.py --steps 2 --warmup 1) > gpurun_out/ncu_launches_final.log 2>&1
-(timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_candidates -s 1 -c 1 -o gpurun_out/prof_tc_final python bench.py --legs eval --steps 1 --warmup 1) > gpurun_out/ncu_tc_final.log 2>&1
-(timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmm_rows -s 3 -c 1 -o gpurun_out/prof_spmm_final python bench.py --legs propagate --steps 1 --warmup 1) > gpurun_out/ncu_spmm_final.log 2>&1
-(timeout 900 ncu --set full --clock-control none -k regex:tc_candidates -s 4 -c 1 -o gpurun_out/prof_tc_knn_final python bench.py --legs knn --steps 2 --warmup 1) > gpurun_out/ncu_tcknn_final.log 2>&1
-ls -la gpurun_out | tail -8
+KREG='regex:rank_topk|spmm_|sddmm|topk_hits|row_norm|row_scale|tc_cand|rescore|to_bf16|max_reduce|slice_merge|degree_inv|gather_rows|bpr_|sample_neg|cooccur'
+(timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -c 600 --csv --log-file gpurun_out/launches_r01_final.csv python bench.py --steps 2 --warmup 1) > gpurun_out/ncu_launches_final.log 2>&1
+cap() {  # name, kernel regex, skip, extra bench args...
+  local name=$1 kre=$2 skip=$3; shift 3
+  (timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$kre" -s "$skip" -c 1 -f -o gpurun_out/prof_$name python bench.py "$@") > gpurun_out/ncu_$name.log 2>&1
+  if [ -f gpurun_out/prof_$name.ncu-rep ]; then
+    ncu -i gpurun_out/prof_$name.ncu-rep --page raw --csv > gpurun_out/prof_${name}_raw.csv 2>/dev/null
+    ncu -i gpurun_out/prof_$name.ncu-rep --page details --csv > gpurun_out/prof_${name}_details.csv 2>/dev/null
+    ncu -i gpurun_out/prof_$name.ncu-rep --page source --csv > gpurun_out/prof_${name}_source.csv 2>/dev/null
+    sz=$(stat -c %s gpurun_out/prof_$name.ncu-rep)
+    if [ "$sz" -gt 12000000 ]; then rm -f gpurun_out/prof_$name.ncu-rep; fi
+  fi
+}
+cap tc_eval tc_candidates 1 --legs eval --steps 1 --warmup 1
+cap spmm_rows spmm_rows 3 --legs propagate --steps 1 --warmup 1
+cap tc_knn tc_candidates 4 --legs knn --steps 2 --warmup 1
+cap rescore_eval rescore 0 --legs eval --steps 1 --warmup 1
+ls -la gpurun_out | tail -20
