@@ -13,6 +13,11 @@ How the three parts of the path shard:
                    numbering; each layer is a local SpMM over the rank's rows followed by one
                    all-gather of the [N/G, d] output blocks into the replicated table.
 
+For the bipartite user-item graph itself there is a cheaper exchange (``BipartiteShard``): users stay on
+their rank for the whole propagation and only the ITEM table moves -- every rank adds up its users'
+contributions to all item rows and one all-reduce of the [I, d] partials per layer replaces the all-gather of
+the whole [U+I, d] table (at the 10M-user / 2M-item config: 0.5 GB instead of 2.7 GB per layer).
+
 Everything here works with the gloo backend on CPU tensors as well (used by the world-size-2
 tests); the compute calls themselves are GPU-only.
 """
@@ -151,3 +156,113 @@ def propagate_mean_sharded(local_graph, part: CyclicPartition, x0_perm: torch.Te
             allgather_blocks(y, nxt, group)
             cur, nxt = nxt, (torch.empty_like(x0_perm) if cur is x0_perm else cur)
     return acc
+
+
+# ---------------------------------------------------------------------------------------------
+# propagation on the bipartite user-item graph: users stay local, the item table is all-reduced
+# ---------------------------------------------------------------------------------------------
+
+
+@dataclass
+class BipartiteShard:
+    """This rank's share of the symmetric user-item graph: users [u_lo, u_hi) and ALL items.
+
+    ``ui``: [U_local, I] block (rows = local users, columns = items), ``iu``: its transpose [I, U_local];
+    the degree scales d^-1/2 are attached as row/col scales (item degrees are global)."""
+    num_user: int
+    num_item: int
+    u_lo: int
+    u_hi: int
+    ui: object
+    iu: object
+    iu_blocks: Optional[list] = None     # [(item_lo, item_hi, graph)]: ``iu`` cut into row blocks, so that the
+                                         # all-reduce of one block runs under the product of the next
+
+
+def build_bipartite_shard(users: torch.Tensor, local_items: torch.Tensor, num_user: int, num_item: int,
+                          group=None, n_blocks: Optional[int] = None) -> BipartiteShard:
+    """Builds the shard from (user, local item) training pairs on the GPU.  ``users`` may hold all pairs (every
+    rank then keeps the pairs of its own user range) or only this rank's."""
+    from . import propagate as P
+    import os
+    rank, world = world_info()
+    if n_blocks is None:
+        # measured at the 100M-edge config: cutting the item rows into 4 blocks (all-reduce of block b under the
+        # product of block b+1) gives 55 -> 64 G edges/s on 8 GPUs, but costs 12 % on 2 GPUs, where the exchange
+        # is short and the smaller launches and NCCL's own CTAs only get in the way
+        n_blocks = int(os.environ.get("CHAOREC_BIPARTITE_BLOCKS", "4" if world >= 4 else "1"))
+    u_lo, u_hi = shard_range(num_user, world, rank)
+    mine = (users >= u_lo) & (users < u_hi)
+    u = (users[mine] - u_lo).to(torch.int64)
+    it = local_items[mine].to(torch.int64)
+    item_deg = torch.bincount(it, minlength=num_item)
+    if world > 1:
+        dist.all_reduce(item_deg, group=group)
+    user_deg = torch.bincount(u, minlength=u_hi - u_lo)
+    dis_u = user_deg.to(torch.float32).pow(-0.5)
+    dis_i = item_deg.to(torch.float32).pow(-0.5)
+    dis_u[torch.isinf(dis_u)] = 0
+    dis_i[torch.isinf(dis_i)] = 0
+    ui = P.csr_from_coo(u, it, None, u_hi - u_lo, num_item)
+    ui.row_scale, ui.col_scale = dis_u, dis_i
+    iu = P.csr_from_coo(it, u, None, num_item, u_hi - u_lo)
+    iu.row_scale, iu.col_scale = dis_i, dis_u
+    blocks = None
+    if world > 1 and n_blocks > 1:
+        blocks = []
+        for b in range(n_blocks):
+            lo, hi = shard_range(num_item, n_blocks, b)
+            e_lo, e_hi = int(iu.rowptr[lo]), int(iu.rowptr[hi])
+            g = P.CSRGraph((iu.rowptr[lo:hi + 1] - iu.rowptr[lo]).contiguous(), iu.col[e_lo:e_hi].contiguous(), None, hi - lo,
+                           u_hi - u_lo).plan_hubs()
+            g.row_scale, g.col_scale = dis_i[lo:hi].contiguous(), dis_u
+            blocks.append((lo, hi, g))
+    return BipartiteShard(num_user, num_item, u_lo, u_hi, ui, iu, blocks)
+
+
+def _cuda_spmm(graph, x: torch.Tensor) -> torch.Tensor:
+    from . import propagate as P
+    y = torch.empty(graph.M, x.shape[1], dtype=torch.float32, device=x.device)
+    P._spmm_raw(graph, x.contiguous(), y, None, 0.0, 0)
+    return y
+
+
+def propagate_mean_bipartite(shard: BipartiteShard, xu_local: torch.Tensor, xi: torch.Tensor, n_layers: int,
+                             alpha: Optional[float] = None, spmm=None, group=None):
+    """L-layer LightGCN propagation + layer mean on a ``BipartiteShard``.
+
+    ``xu_local``: layer-0 rows of this rank's users [U_local, d]; ``xi``: the replicated layer-0 item table
+    [I, d].  Per layer: user rows from the item table (local), partial item rows from the local users, one
+    all-reduce (sum) of the item partials.  Returns (mean over layers of the local user rows, of all item rows).
+    ``spmm(graph, x)`` defaults to the CUDA kernel; the gloo tests pass a CPU product."""
+    rank, world = world_info()
+    if alpha is None:
+        alpha = 1.0 / (n_layers + 1)
+    acc_u, acc_i = xu_local * alpha, xi * alpha
+    xu, xi_cur = xu_local, xi
+    for l in range(n_layers):
+        last = l == n_layers - 1
+        # item partials first, block by block: the all-reduce of a block runs under the products that follow
+        works = []
+        if spmm is None and shard.iu_blocks and world > 1:
+            from . import propagate as P
+            yi = torch.empty_like(acc_i)
+            for lo, hi, g in shard.iu_blocks:
+                P._spmm_raw(g, xu.contiguous(), yi[lo:hi], None, 0.0, 0)
+                works.append(dist.all_reduce(yi[lo:hi], group=group, async_op=True))
+        else:
+            yi = (spmm or _cuda_spmm)(shard.iu, xu)
+            if world > 1:
+                works.append(dist.all_reduce(yi, group=group, async_op=True))
+        if spmm is None:
+            from . import propagate as P
+            yu = None if last else torch.empty_like(acc_u)
+            P._spmm_raw(shard.ui, xi_cur.contiguous(), yu, acc_u, alpha, 0)      # acc_u += alpha * yu, fused
+        else:
+            yu = spmm(shard.ui, xi_cur)
+            acc_u.add_(yu, alpha=alpha)
+        for w in works:
+            w.wait()
+        acc_i.add_(yi, alpha=alpha)
+        xu, xi_cur = yu, yi
+    return acc_u, acc_i

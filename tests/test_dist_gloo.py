@@ -13,6 +13,7 @@ import torch.multiprocessing as mp
 import chaorec_b200 as cb
 from chaorec_b200 import dist as cdist
 from conftest import load_golden, metrics_array, rows_to_object_array
+from oracle import ref_ops
 
 
 def _free_port():
@@ -85,6 +86,28 @@ def _worker(rank, world, port, results):
         got = part.unpermute_rows(out_perm)
         if rank == 0:
             results["prop_err"] = float((got - want).abs().max() / want.abs().max())
+
+        # --- bipartite propagation: users stay local, item partials are all-reduced ----------------
+        U, I, d, L = 203, 57, 8, 3
+        tu, ti = ref_ops.synth_interactions(U, I, 1500, 5)
+        ei = ref_ops.symmetrise_edges(torch.stack((tu, ti + U), 1).numpy())
+        gen = torch.Generator().manual_seed(6)
+        xu0, xi0 = torch.randn(U, d, generator=gen), torch.randn(I, d, generator=gen)
+        want = ref_ops.lightgcn_forward(xu0, xi0, ei, L)
+        u_lo, u_hi = cdist.shard_range(U, world, rank)
+        mine = (tu >= u_lo) & (tu < u_hi)
+        lu, li = tu[mine] - u_lo, ti[mine]
+        item_deg = torch.bincount(ti, minlength=I).float()
+        user_deg = torch.bincount(lu, minlength=u_hi - u_lo).float()
+        w = user_deg.pow(-0.5)[lu] * item_deg.pow(-0.5)[li]
+        shard = cdist.BipartiteShard(U, I, u_lo, u_hi,
+                                     torch.sparse_coo_tensor(torch.stack((lu, li)), w, (u_hi - u_lo, I)),
+                                     torch.sparse_coo_tensor(torch.stack((li, lu)), w, (I, u_hi - u_lo)))
+        au, ai = cdist.propagate_mean_bipartite(shard, xu0[u_lo:u_hi].clone(), xi0.clone(), L, spmm=torch.sparse.mm)
+        all_u = cdist.allgather_concat(au)
+        if rank == 0:
+            got = torch.cat((all_u, ai))
+            results["bip_err"] = float((got - want).abs().max() / want.abs().max())
     finally:
         dist.destroy_process_group()
 
@@ -95,6 +118,7 @@ def test_world_size_2_sharding_and_collectives():
     mp.spawn(_worker, args=(2, _free_port(), results), nprocs=2, join=True)
     assert results["metrics_ok"] is True
     assert results["prop_err"] < 1e-5
+    assert results["bip_err"] < 1e-5
 
 
 def test_shard_range_covers_everything():
