@@ -212,114 +212,6 @@ __global__ void __launch_bounds__(TPB, MINB) spmm_rows_kernel(const SpmmArgs a) 
     rows_body<LANES, NV, TPB>(a, blockIdx.x);
 }
 
-// Short rows (a user's ~12 items) are latency-bound when a sub-warp walks them one at a time:
-// rowptr -> column indices -> gathers is a chain of dependent loads per row.  Here a sub-warp owns
-// kRowsPerGroup CONSECUTIVE rows, whose edges are one contiguous CSR range, and streams that range
-// like a hub chunk: column indices of the next 16 edges are prefetched while the current ones are
-// gathered (eight 256-byte gathers in flight), the accumulator is flushed at row boundaries.
-constexpr int kRowsPerGroup = 8;
-
-template <int LANES, int NV>
-__global__ void __launch_bounds__(kThreads) spmm_rows_seg_kernel(const SpmmArgs a) {
-    static_assert(LANES > kRowsPerGroup, "one lane per rowptr entry of the block");
-    constexpr int kGroups = kThreads / LANES;
-    const int lane = threadIdx.x & 31;
-    const int gl = threadIdx.x % LANES;
-    const unsigned mask = group_mask<LANES>(lane);
-    const int64_t r0 = (static_cast<int64_t>(blockIdx.x) * kGroups + threadIdx.x / LANES) * kRowsPerGroup;
-    if (r0 >= a.M) return;
-    const int nrows = (a.M - r0 < kRowsPerGroup) ? static_cast<int>(a.M - r0) : kRowsPerGroup;
-    const int64_t myptr = __ldg(a.rowptr + r0 + (gl <= nrows ? gl : nrows));   // lane i: rowptr[r0 + i]
-    const int64_t e_lo = __shfl_sync(mask, myptr, 0, LANES);
-    const int64_t e_hi = __shfl_sync(mask, myptr, nrows, LANES);
-    float4 acc[NV];
-    // a block that contains a hub row (taken by the hub kernels) falls back to row-at-a-time
-    const int64_t mydeg = __shfl_down_sync(mask, myptr, 1, LANES) - myptr;
-    const bool has_hub = a.hub_rows != nullptr && __any_sync(mask, gl < nrows && mydeg > a.hub_threshold);
-    if (has_hub) {
-        for (int i = 0; i < nrows; ++i) {
-            const int64_t lo = __shfl_sync(mask, myptr, i, LANES), hi = __shfl_sync(mask, myptr, i + 1, LANES);
-            if (hi - lo > a.hub_threshold) continue;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-            gather_edges<LANES, NV, false>(a, lo, hi, gl, mask, acc);
-            row_epilogue<LANES, NV>(a, r0 + i, gl, acc);
-        }
-        return;
-    }
-#pragma unroll
-    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int cur = 0;
-    int64_t row_end = __shfl_sync(mask, myptr, 1, LANES);
-    // prefetch the first chunk of column indices / values
-    int c_nxt = 0;
-    float v_nxt = 1.0f;
-    if (e_lo + gl < e_hi) {
-        c_nxt = __ldg(a.col + e_lo + gl);
-        if (a.val) v_nxt = __ldg(a.val + e_lo + gl);
-    }
-    for (int64_t e0 = e_lo; e0 < e_hi; e0 += LANES) {
-        const int c = c_nxt;
-        float w = v_nxt;
-        if (a.col_scale) w *= __ldg(a.col_scale + c);          // issued together with the gathers below
-        const int64_t en = e0 + LANES + gl;
-        c_nxt = 0;
-        v_nxt = 1.0f;
-        if (en < e_hi) {                                       // next chunk's indices: off the critical path
-            c_nxt = __ldg(a.col + en);
-            if (a.val) v_nxt = __ldg(a.val + en);
-        }
-        const int cnt = (e_hi - e0 < LANES) ? static_cast<int>(e_hi - e0) : LANES;
-        for (int j = 0; j < cnt; j += 8) {
-            const int nb = (cnt - j < 8) ? (cnt - j) : 8;
-            int cj[8];
-            float wj[8];
-            float4 xv[8][NV];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                cj[t] = __shfl_sync(mask, c, (j + t) % LANES, LANES);
-                wj[t] = __shfl_sync(mask, w, (j + t) % LANES, LANES);
-            }
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                if (t < nb) {
-                    const float4 *xr = a.x + static_cast<int64_t>(cj[t]) * a.dq;
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        const int q = gl + v * LANES;
-                        xv[t][v] = (q < a.dq) ? __ldg(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                if (t < nb) {
-                    const int64_t ee = e0 + j + t;
-                    while (ee == row_end) {                    // row boundary (loops over empty rows)
-                        row_epilogue<LANES, NV>(a, r0 + cur, gl, acc);
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        ++cur;
-                        row_end = __shfl_sync(mask, myptr, cur + 1, LANES);
-                    }
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        acc[v].x = fmaf(wj[t], xv[t][v].x, acc[v].x);
-                        acc[v].y = fmaf(wj[t], xv[t][v].y, acc[v].y);
-                        acc[v].z = fmaf(wj[t], xv[t][v].z, acc[v].z);
-                        acc[v].w = fmaf(wj[t], xv[t][v].w, acc[v].w);
-                    }
-                }
-            }
-        }
-    }
-    for (; cur < nrows; ++cur) {                               // last row and trailing empty rows
-        row_epilogue<LANES, NV>(a, r0 + cur, gl, acc);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-}
-
 // ---- hot-column staging -----------------------------------------------------------------------
 // Both the sub-warp kernel and the hub kernels top out near 6 TB/s of L2->SM traffic whether the
 // gathers hit in L2 or go to HBM (profiles/: rows kernel 45 GB in 8.5 ms, hub chunks 17 GB from
@@ -541,10 +433,6 @@ int launch_spmm(const SpmmArgs &a, const HotArgs &h, int64_t n_hub_chunks, cudaS
             return CHAOREC_E_LAUNCH;
         }
         spmm_rows_hot_kernel<LANES, NV><<<sm_count(), 1024, smem, st>>>(a, h);
-    } else
-    if constexpr (LANES > kRowsPerGroup && false) {   // measured slower (80 regs, 10.1 ms vs 8.5 ms at the 100M-edge config)
-        const int64_t seg_blocks = (a.M + static_cast<int64_t>(kGroups) * kRowsPerGroup - 1) / (static_cast<int64_t>(kGroups) * kRowsPerGroup);
-        if (seg_blocks > 0) spmm_rows_seg_kernel<LANES, NV><<<static_cast<unsigned>(seg_blocks), kThreads, 0, st>>>(a);
     } else if (a.hub_counters != nullptr && a.hub_rows != nullptr && n_hub_chunks > 0) {
         if (blocks + n_hub_chunks > 0x7fffffffLL) return CHAOREC_E_UNSUPPORTED;
         spmm_fused_kernel<LANES, NV><<<static_cast<unsigned>(blocks + n_hub_chunks), kThreads, 0, st>>>(a);
