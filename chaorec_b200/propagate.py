@@ -369,6 +369,10 @@ def bipartite_graph(users: torch.Tensor, local_items: torch.Tensor, num_user: in
     "v2"     FREEDOM.get_norm_adj_mat, Model/FREEDOM.py:73-83        (2deg)^-1/2[r] * (2deg)^-1/2[c]  (half of v1)
     "v3"     FREEDOM._normalize_adj_m + mirror, Model/FREEDOM.py:85-100,153-162
                                                                       (deg+1e-7)^-1/2[r] * (deg+1e-7)^-1/2[c]
+    "v4"     scipy-dok get_norm_adj_mat, Model/SimGCL.py:64-104 (+12 copies)
+                                                                      as v3 with the power taken in fp64, then fp32
+    "v5"     scipy-lil get_adj_mat, Model/MGCN.py:164-196            deg^-1/2 in fp32, empty rows -> (1e-16)^-1/2
+                                                                      (never multiplied by an edge) = v1
     The weights are never materialised: they are the row/col scales the SpMM kernel applies.
     """
     _lib.require_cuda(users, "users")
@@ -385,8 +389,12 @@ def bipartite_graph(users: torch.Tensor, local_items: torch.Tensor, num_user: in
                    "chaorec_degree_inv_sqrt")
     if variant == "v2":
         dis = dis * (2.0 ** -0.5)
-    elif variant not in ("v1", "v3"):
-        raise ValueError("variant must be 'v1', 'v2' or 'v3'")
+    elif variant == "v4":
+        # np.power(deg + 1e-7, -0.5) in float64 (Model/SimGCL.py:83-85); the reference then rounds the PRODUCT
+        # d[r]*d[c] to fp32, here each factor is rounded (difference <= 2^-23 relative per edge)
+        dis = ((g.rowptr[1:] - g.rowptr[:-1]).to(torch.float64) + 1e-7).pow(-0.5).to(torch.float32)
+    elif variant not in ("v1", "v3", "v5"):
+        raise ValueError("variant must be 'v1' .. 'v5'")
     g.row_scale = g.col_scale = dis
     g.symmetric = True
     return g

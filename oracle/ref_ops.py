@@ -470,3 +470,39 @@ def user_graph_topk(C: np.ndarray, k: int = 200):
         order = np.lexsort((np.arange(row.size), -row))[:kk]
         out[u] = [order.tolist(), [float(row[v]) for v in order]]
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# scipy adjacency builders V4 / V5.  The reference's own code cannot run here
+# (dok_matrix._update was removed from scipy), so these restate the published formulas: UNPINNED.
+# ---------------------------------------------------------------------------------------------
+def scipy_norm_adj_v4(train_u: np.ndarray, train_i_local: np.ndarray, num_user: int, num_item: int) -> torch.Tensor:
+    """Model/SimGCL.py:64-104: A = [[0,R],[R^T,0]] with ones; diag = ((A>0).sum(1) + 1e-7)^-0.5 in float64;
+    L = D @ A @ D in float64, cast to float32 -> torch sparse COO."""
+    import scipy.sparse as sp
+    n = num_user + num_item
+    r = np.concatenate((train_u, train_i_local + num_user))
+    c = np.concatenate((train_i_local + num_user, train_u))
+    A = sp.coo_matrix((np.ones(r.size, dtype=np.float32), (r, c)), shape=(n, n)).tocsr()
+    A.data[:] = 1.0                                            # dok semantics: duplicates collapse to one entry
+    diag = np.power(np.asarray((A > 0).sum(axis=1)).flatten() + 1e-7, -0.5)
+    L = sp.coo_matrix(sp.diags(diag) @ A @ sp.diags(diag))
+    idx = torch.tensor(np.array([L.row, L.col]), dtype=torch.long)
+    return torch.sparse_coo_tensor(idx, torch.FloatTensor(L.data), (n, n), dtype=torch.float32)
+
+
+def scipy_norm_adj_v5(train_u: np.ndarray, train_i_local: np.ndarray, num_user: int, num_item: int) -> torch.Tensor:
+    """Model/MGCN.py:164-196: float32 adjacency, rowsum == 0 -> 1e-16, d = rowsum^-0.5 (inf -> 0), D A D."""
+    import scipy.sparse as sp
+    n = num_user + num_item
+    r = np.concatenate((train_u, train_i_local + num_user))
+    c = np.concatenate((train_i_local + num_user, train_u))
+    A = sp.coo_matrix((np.ones(r.size, dtype=np.float32), (r, c)), shape=(n, n)).tocsr()
+    A.data[:] = 1.0
+    rowsum = np.array(A.sum(1))
+    rowsum[rowsum == 0.] = 1e-16
+    d_inv = np.power(rowsum, -0.5).flatten()
+    d_inv[np.isinf(d_inv)] = 0.
+    L = sp.diags(d_inv).dot(A).dot(sp.diags(d_inv)).tocoo()
+    idx = torch.tensor(np.array([L.row, L.col]), dtype=torch.long)
+    return torch.sparse_coo_tensor(idx, torch.tensor(L.data, dtype=torch.float32), (n, n))

@@ -282,6 +282,12 @@ def test_device_side_adjacency_builders_match_reference_fixture():
     v1 = cb.bipartite_graph(tr[:, 0], tr[:, 1] - U1, U1, I1, "v1")
     x1 = torch.from_numpy(np.concatenate([l["user_w"], l["item_w"]])).to(dev())
     assert rel_err(cb.propagate_mean(v1, x1, int(l["n_layers"])), torch.from_numpy(l["result"])) <= REL
+    # V4 / V5: the scipy builders of SimGCL & co. / MGCN (restated in the oracle; the reference's code needs scipy 1.10)
+    tu4, ti4 = tr[:, 0].cpu(), (tr[:, 1] - U1).cpu()
+    for variant, build in (("v4", ref_ops.scipy_norm_adj_v4), ("v5", ref_ops.scipy_norm_adj_v5)):
+        gv = cb.bipartite_graph(tr[:, 0], tr[:, 1] - U1, U1, I1, variant)
+        want = torch.sparse.mm(build(tu4.numpy(), ti4.numpy(), U1, I1), x1.cpu())
+        assert rel_err(cb.spmm(gv, x1), want) <= REL
     # resampling keeps int(E*(1-p)) distinct edges and renormalises them (structure-level check)
     vals = torch.ones(train.shape[0], device=dev())
     rg = cb.resample_masked_graph(train[:, 0], train[:, 1] - U, vals, U, I, 0.3, torch.Generator(device=dev()).manual_seed(1))
