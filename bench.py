@@ -311,7 +311,7 @@ def run_eval_leg(args, dev, rank, world, peaks):
         e2e=dict(value=e2e_value, unit="users/s", h2d_bytes_per_step=batch.h2d_bytes(), d2h_bytes_per_step=n_local * 8,
                  includes="H2D of embeddings+mask+positives, rank kernel, hits kernel, D2H hit masks, gather, host fp64 metrics"),
         roofline=roof, engine=st.get("engine"),
-        gpu_launches=(10 if tensor else 2) * args.steps,
+        gpu_launches=(11 if tensor else 2) * args.steps,   # to_bf16 x2, max_reduce, gather_rows, tc_candidates x2, rescore, rank_topk x2 + slice_merge (fallback rows), topk_hits
         config=dict(workload="full-rank top-20 eval, 1M users x 200k items, d=64 (BASELINE configs[3])", users=U, items=I,
                     d=d, topk=K, mask_items_per_user=EVAL_CFG["mask_per_user"], sharding=f"users/{world}",
                     l2="flushed between steps (192 MiB write)", scale=args.scale),

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import weakref
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, Iterable, Optional, Sequence, Tuple
 
@@ -97,17 +98,40 @@ def rank_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, mask: Optional[Mas
     return (out_idx, out_score) if return_scores else out_idx
 
 
-_mask_cache: Dict[int, Tuple[weakref.ref, int, MaskCSR]] = {}
+# Conversions of the reference's python containers are cached per OBJECT.  Every entry holds a strong reference
+# to the object it was built from: an id() alone can be handed to a new object of the same length once the old
+# one is collected (which made two consecutive val/test arrays share one conversion).  A few entries only.
+_mask_cache: "OrderedDict[int, Tuple[object, int, MaskCSR]]" = OrderedDict()
+_CACHE_ENTRIES = 8
+
+
+def _cache_get(cache, obj, device):
+    hit = cache.get(id(obj))
+    if hit is not None and hit[0] is obj and hit[1] == len(obj) and hit[2].rowptr.device == device:
+        cache.move_to_end(id(obj))
+        return hit[2]
+    return None
+
+
+def _cache_put(cache, obj, value):
+    cache[id(obj)] = (obj, len(obj), value)
+    cache.move_to_end(id(obj))
+    while len(cache) > _CACHE_ENTRIES:
+        cache.popitem(last=False)
+
+
+def clear_caches() -> None:
+    """Drop the cached CSR conversions (call it after mutating ``user_item_dict`` / ``val_data`` in place)."""
+    _mask_cache.clear()
+    _pos_cache.clear()
 
 
 def _model_mask(model, device) -> MaskCSR:
     d = model.user_item_dict
-    key = id(d)
-    hit = _mask_cache.get(key)
-    if hit is not None and hit[1] == len(d) and hit[2].rowptr.device == device:
-        return hit[2]
-    m = build_mask_csr(d, model.num_user, model.num_item, device)
-    _mask_cache[key] = (None, len(d), m)
+    m = _cache_get(_mask_cache, d, device)
+    if m is None:
+        m = build_mask_csr(d, model.num_user, model.num_item, device)
+        _cache_put(_mask_cache, d, m)
     return m
 
 
@@ -138,14 +162,13 @@ class PositivesCSR:
     n_pos: np.ndarray           # int32 [n_rows] len(data[1:]) incl. duplicates (host)
 
 
-_pos_cache: Dict[int, Tuple[int, PositivesCSR]] = {}
+_pos_cache: "OrderedDict[int, Tuple[object, int, PositivesCSR]]" = OrderedDict()
 
 
 def build_positives_csr(data: Sequence[Sequence[int]], device: torch.device) -> PositivesCSR:
-    key = id(data)
-    hit = _pos_cache.get(key)
-    if hit is not None and hit[0] == len(data) and hit[1].rowptr.device == device:
-        return hit[1]
+    cached = _cache_get(_pos_cache, data, device)
+    if cached is not None:
+        return cached
     n = len(data)
     lens = np.fromiter((len(r) - 1 for r in data), dtype=np.int64, count=n)
     flat = np.fromiter((v for r in data for v in r), dtype=np.int64, count=int(lens.sum()) + n)
@@ -161,7 +184,7 @@ def build_positives_csr(data: Sequence[Sequence[int]], device: torch.device) -> 
     order = np.lexsort((pos, row_of))
     out = PositivesCSR(torch.from_numpy(row_user).to(device), torch.from_numpy(rowptr).to(device),
                        torch.from_numpy(pos[order]).to(device), lens.astype(np.int32))
-    _pos_cache[key] = (n, out)
+    _cache_put(_pos_cache, data, out)
     return out
 
 

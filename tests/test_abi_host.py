@@ -157,3 +157,28 @@ def test_cuda_entry_points_refuse_cpu_tensors():
         cb.sample_negatives(torch.zeros(4, dtype=torch.int64), None, 8, 0)
     with pytest.raises(RuntimeError):
         cb.user_cooccurrence_topk(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64), 4, 4)
+
+
+def test_conversion_caches_are_keyed_by_object_identity_not_by_a_recyclable_id():
+    """A cached CSR conversion must never be served for a different container that happens to reuse the id()
+    and length of a collected one (two consecutive val/test arrays did exactly that)."""
+    import types
+    from collections import OrderedDict
+    import numpy as np
+    import torch
+    from chaorec_b200 import ranking
+    cache = OrderedDict()
+    dev = torch.device("cpu")
+    fake = lambda tag: types.SimpleNamespace(rowptr=torch.zeros(1), tag=tag)      # noqa: E731
+    first = np.empty(5, dtype=object)
+    ranking._cache_put(cache, first, fake("first"))
+    assert ranking._cache_get(cache, first, dev).tag == "first"
+    ident = id(first)
+    del first                                           # the entry keeps the array alive: its id cannot be recycled
+    assert cache[ident][0] is not None
+    for _ in range(64):                                 # same shape, same length: must always miss
+        other = np.empty(5, dtype=object)
+        assert id(other) != ident and ranking._cache_get(cache, other, dev) is None
+    for i in range(20):                                 # bounded
+        ranking._cache_put(cache, np.empty(3, dtype=object), fake(i))
+    assert len(cache) <= ranking._CACHE_ENTRIES
