@@ -54,6 +54,9 @@ SIGNATURES = {
 _lib = None
 
 
+ABI_VERSION = 2      # CHAOREC_ABI_VERSION of include/chaorec_b200.h this binding was written against
+
+
 def load() -> C.CDLL:
     """Loads the CUDA library (once).  Raises RuntimeError when it has not been built."""
     global _lib
@@ -67,7 +70,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.chaorec_abi_version() != 1:
+        if lib.chaorec_abi_version() != ABI_VERSION:
             raise RuntimeError("libchaorec_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -297,7 +297,7 @@ def propagate_mean(adj, x0: torch.Tensor, n_layers: int, include_layer0: bool = 
     return _PropagateMeanFn.apply(x0, g, int(n_layers), float(alpha), bool(include_layer0))
 
 
-_edge_cache: Dict[Tuple[int, int, int], Tuple[weakref.ref, CSRGraph]] = {}
+_edge_cache: Dict[Tuple[int, int, int], Tuple[weakref.ref, CSRGraph, int]] = {}
 
 
 def graph_from_edge_index(edge_index: torch.Tensor, num_nodes: int) -> CSRGraph:
@@ -305,7 +305,7 @@ def graph_from_edge_index(edge_index: torch.Tensor, num_nodes: int) -> CSRGraph:
     with deg = degree(row).  CSR rows are destinations (``edge_index[1]``), columns sources."""
     key = (id(edge_index), edge_index.data_ptr(), num_nodes)
     hit = _edge_cache.get(key)
-    if hit is not None and hit[0]() is edge_index:
+    if hit is not None and hit[0]() is edge_index and hit[2] == edge_index._version:   # same tensor, not written since
         return hit[1]
     _lib.require_cuda(edge_index, "edge_index")
     lib = _lib.load()
@@ -329,7 +329,7 @@ def graph_from_edge_index(edge_index: torch.Tensor, num_nodes: int) -> CSRGraph:
     if len(_edge_cache) > 16:
         for k in [k for k, v in _edge_cache.items() if v[0]() is None]:
             _edge_cache.pop(k, None)
-    _edge_cache[key] = (weakref.ref(edge_index), g)
+    _edge_cache[key] = (weakref.ref(edge_index), g, edge_index._version)
     return g
 
 

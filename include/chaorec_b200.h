@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CHAOREC_ABI_VERSION 1
+#define CHAOREC_ABI_VERSION 2   /* 2: hub plan arguments of the SpMM entry points, new entry points */
 
 enum {
     CHAOREC_OK = 0,
