@@ -90,7 +90,9 @@ int64_t chaorec_spmm_hub_row_chunks(int64_t row_nnz, int32_t chunk);
  * the defaults.  hub_counters (nullable, int32 [n_hub], zero before the first call; the kernel leaves
  * it zero) selects the single-launch mode meant for small graphs: row CTAs and hub-chunk CTAs share one
  * grid and the CTA that completes a hub row's last chunk sums its partials (in chunk order: results do
- * not depend on scheduling).  Without it hub rows take two extra launches.  With hub_rows == NULL
+ * not depend on scheduling).  The counters are launch state: a hub_counters buffer must not be shared by
+ * launches that may run concurrently (different streams); every other argument is read-only or
+ * caller-owned output, so the entry point is otherwise re-entrant.  Without it hub rows take two extra launches.  With hub_rows == NULL
  * every row takes the sub-warp path (correct, slow for very long rows).
  * row_order (nullable, int32 [M], a permutation of the rows): the order in which sub-warps take rows.
  * Sorting rows by length (longest first) puts rows of equal length in the same warp and CTA, which
