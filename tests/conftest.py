@@ -13,6 +13,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The tests need the in-tree C-ABI library.  Where nvcc is present (the authoring container) make sure it is
+    # built and current; on the GPU box the prebuilt .so travels with the snapshot.  This is test setup only: the
+    # product itself never builds on demand, it raises when the library is missing.
+    import shutil
+    if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+        from chaorec_b200.build import build_cuda
+        build_cuda()
 
 
 def pytest_collection_modifyitems(config, items):
