@@ -24,9 +24,8 @@ tests); the compute calls themselves are GPU-only.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

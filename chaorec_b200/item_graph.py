@@ -12,7 +12,7 @@ product is the SpMM kernel, differentiable in the edge values (SDDMM again) and 
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 

@@ -12,7 +12,6 @@ csrc/rank_topk.cu and csrc/hits_metrics.cu through the C ABI.
 from __future__ import annotations
 
 import ctypes as C
-import weakref
 from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, Iterable, Optional, Sequence, Tuple
