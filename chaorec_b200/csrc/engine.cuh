@@ -38,4 +38,10 @@ bool tc_supported(int64_t Ma, int64_t Nb, int D, int K);
 size_t tc_workspace_bytes(int64_t Ma, int64_t Nb, int D);
 int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes, cudaStream_t stm);
 
+// d <= 64: fp16 TS-form tcgen05 pre-filter with per-row-block accumulator slots (tc_eval.cu); tc_topk_launch
+// dispatches to it
+bool tc_eval_supported(int64_t Ma, int64_t Nb, int D, int K);
+size_t tc_eval_workspace_bytes(int64_t Ma, int64_t Nb, int D);
+int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes, cudaStream_t stm);
+
 }  // namespace chaorec

@@ -942,6 +942,7 @@ int tc_choose_slices(int64_t Ma, int64_t Nb, int D) {
 }
 
 size_t tc_workspace_bytes(int64_t Ma, int64_t Nb, int D) {
+    if (D <= BK) return tc_eval_workspace_bytes(Ma, Nb, D);
     const HostShape hs = host_shape(D);
     const int slices = tc_choose_slices(Ma, Nb, D);
     size_t n = 256;                                                    // counters
@@ -960,12 +961,14 @@ size_t tc_workspace_bytes(int64_t Ma, int64_t Nb, int D) {
 }
 
 bool tc_supported(int64_t Ma, int64_t Nb, int D, int K) {
+    if (D <= BK) return tc_eval_supported(Ma, Nb, D, K);
     // small problems stay on the exact engine (nothing to win, and K' must be well below Nb)
     return D % 8 == 0 && D >= 8 && K >= 1 && K <= 64 && Nb >= 1024 && Ma >= 1 && Ma < 0x7FFFFFF0LL && encode_fn() != nullptr;
 }
 
 // A, B: fp32 operands (same pointer allowed).  Computes exact canonical top-K of every row of A.
 int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes, cudaStream_t stm) {
+    if (e.d <= BK) return tc_eval_launch(e, workspace, workspace_bytes, stm);
     if (workspace_bytes < tc_workspace_bytes(e.Ma, e.Nb, e.d)) return CHAOREC_E_WORKSPACE;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     unsigned int *counters = reinterpret_cast<unsigned int *>(ws); ws += 256;

@@ -1,0 +1,1067 @@
+// K2 tensor engine for d <= 64 (full-ranking evaluation, Model/LightGCN.py:147-155; also the 64-d item
+// graphs of Model/LATTICE.py:46-52): fp16 tcgen05 pre-filter with a fused threshold epilogue, exact fp32
+// re-score and certification.  Replaces the round-1 `tc_candidates_kernel<true>`.
+//
+// What changed against round 1, and the measurement behind each change (profiles/r02_probe_*.log):
+//   * A operand in TENSOR MEMORY (tcgen05.mma "TS" form).  A 128x64x16 MMA with both operands in shared memory
+//     reads 6 KB per instruction and is bound by the 128 B/clk shared-memory port at ~50 clk; with the 512 user
+//     rows of a unit parked in 128 TMEM columns (written once per unit by the rows' own epilogue threads with
+//     tcgen05.st) only the 2 KB item slab is read: 34 clk per MMA = the nominal tensor peak.
+//   * TWO issuing warps, warp-uniform control flow with an ELECTed lane.  `if (lane == 0)` around tcgen05.mma
+//     makes the compiler wrap every MMA in an R2UR/BRA.U.ANY loop (72 clk per MMA); one converged warp still
+//     needs ~50 clk between dispatches, two warps (row blocks 0-1 / 2-3) reach 34.
+//   * SIX accumulator slots of 128 rows x 64 columns with their own full/empty barriers instead of two
+//     512-row stages: a row block is handed back as soon as its four warps have read it.
+//   * fp16 operands, each user row and the item table scaled by a power of two (exact): 2^-11 relative operand
+//     error instead of bf16's 2^-8, so the certification margin eps shrinks four-fold.
+//   * The epilogue keeps candidates only: per 64 scores, eight 8-column maxima (FMNMX3 trees) and one test;
+//     a warp looks at individual columns only in 8-column groups where one of its rows beats its threshold.
+//     No sort, no mask look-ups, no list hand-over inside the MMA kernel: lists live in their final place
+//     in global memory and the unit's last act is two 4-byte stores per row.  Sorting, mask removal and the
+//     top-K' cut moved into the re-score kernel (a plain SIMT kernel that is not on the tensor pipeline).
+//   * The sample pre-pass is the same kernel in SEED mode over every `stride`-th column tile: the epilogue
+//     keeps the 16 largest TILE MAXIMA of each row in registers (a branch-free insertion network) -- the k-th
+//     largest tile maximum is a lower bound of the k-th largest sample score -- and never touches memory.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "engine.cuh"
+#include "tc_ptx.cuh"
+
+namespace chaorec {
+namespace {
+using namespace ptx;
+
+constexpr int EV_BM = 512;                        // user rows per unit (4 MMA row blocks)
+constexpr int EV_BN = 64;                         // item columns per tile
+constexpr int EV_RB = 4;
+constexpr int EV_KPAD = 64;                       // inner dimension of the fp16 copies (d zero-padded)
+constexpr int EV_STAGES = 12;                     // item-slab ring
+constexpr int EV_STAGE_BYTES = EV_BN * EV_KPAD * 2;
+constexpr int EV_SLOTS = 6;                       // accumulator slots (128 lanes x 64 columns each)
+constexpr int EV_ACC0 = 128;                      // TMEM columns [0,128) hold A: row block rb at 32*rb
+constexpr int EV_CAP = 256;                       // list capacity per (row, slice)
+constexpr int EV_TRIGGER = EV_CAP - 64;           // a tile appends at most 64 entries
+constexpr int EV_EPI_WARPS = 16;
+constexpr int EV_TMA_WARP = 16;
+constexpr int EV_MMA_WARP0 = 17;                  // warps 17, 18 issue the MMAs of row blocks 0-1 / 2-3
+constexpr int EV_THREADS = 20 * 32;              // warp 19 idles: setmaxnreg works on whole warpgroups
+constexpr int EV_REGS_ROLE = 32;                  // registers per thread after setmaxnreg: role warpgroup
+constexpr int EV_REGS_EPI = 112;                  // ... and the four epilogue warpgroups (96 at launch)
+constexpr int EV_SEEDK = 16;                      // tile maxima kept per row in seed mode
+constexpr int EV_STG = 28;                        // entries of a row's shared-memory staging buffer
+constexpr int EV_STG_BYTES = EV_STG * 8;
+constexpr int EV_STG_LIMIT = (EV_STG - 8) * 8;    // flush before a group of 8 appends could overflow it
+constexpr int EV_NUM_BARS = 2 * EV_STAGES + 4 * EV_SLOTS + EV_RB;
+constexpr uint32_t EV_IDESC = make_idesc_m128(EV_BN, /*f32 acc*/ 1, /*f16 operands*/ 0);
+constexpr int EV_KP_MAX = 128;
+
+struct EvalArgs {
+    int64_t Ma, Nb;
+    int n_row_tiles, n_slices, tiles_per_slice, n_col_tiles;
+    int n_seed_tiles, seed_stride, seed_off, seed_k;   // seed mode: tile i of a unit = seed_off + i * seed_stride
+    const __half *a16;            // [Ma][64] scaled fp16 rows
+    const int64_t *mask_rowptr;   // only the row lengths are used here
+    int exclude_self;
+    int kp;
+    uint64_t *lists;              // [Ma][n_slices][EV_CAP] raw entries (score bits << 32 | column), 2 KB aligned
+    int32_t *cnt_out;             // [Ma][n_slices]
+    float *tau_out;               // [Ma][n_slices] threshold in force at the end of the unit (+inf: row gave up)
+    float *tau0;                  // [Ma] starting thresholds: written in seed mode, read in main mode (nullable)
+    unsigned int *dbg;            // [0] = pipeline time-out flag, [1..7] = first time-out record (see ev_wait)
+};
+
+// Every mbarrier wait of the pipeline is bounded: a protocol error (or a lost TMA / MMA completion) must end in a
+// reported failure, never in a hung GPU.  The fast path is one try_wait; only a wait that has to retry reads the
+// clock and the CTA's abort flag.  On a time-out the CTA records which wait failed (role/kind/index/parity, the
+// work position and the barrier word), raises the flag -- every later wait of the CTA then returns at once and the
+// kernel runs to completion on garbage -- and the re-score kernel sends ALL rows to the exact engine, so results
+// stay correct; `dbg[0] != 0` is surfaced through the host shim's stats.
+constexpr unsigned long long EV_WAIT_NS = 4000000000ull;   // 4 s
+// Debug builds (-DCHAOREC_EV_TRACE): every warp keeps a (position << 8 | marker) word in shared memory; the first
+// time-out of a CTA dumps all of them after the record.
+#ifdef CHAOREC_EV_TRACE
+#define EV_TRACE(marker, posv) do { if (lane == 0) s_trace[warp] = (static_cast<uint32_t>(posv) << 8) | (marker); } while (0)
+#else
+#define EV_TRACE(marker, posv) do { } while (0)
+#endif
+__device__ __forceinline__ void ev_wait_slow(uint64_t *bar, uint32_t parity, volatile uint32_t *s_abort, unsigned int *dbg,
+                                          uint32_t code, uint32_t pos) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (!mbar_try_wait(bar, parity)) {
+        if (*s_abort) return;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > EV_WAIT_NS) {
+            *s_abort = 1u;
+            if (dbg != nullptr && atomicExch(&dbg[0], 1u) == 0u) {
+                dbg[1] = code;
+                dbg[2] = pos;
+                dbg[3] = blockIdx.x;
+                dbg[4] = parity;
+                const unsigned long long w = *reinterpret_cast<volatile unsigned long long *>(bar);
+                dbg[5] = static_cast<unsigned int>(w);
+                dbg[6] = static_cast<unsigned int>(w >> 32);
+                dbg[7] = threadIdx.x;
+#ifdef CHAOREC_EV_TRACE
+                for (int w = 0; w < 20; ++w) dbg[8 + w] = s_abort[1 + w];
+#endif
+            }
+            return;
+        }
+    }
+}
+__device__ __forceinline__ void ev_wait(uint64_t *bar, uint32_t parity, volatile uint32_t *s_abort, unsigned int *dbg, uint32_t code,
+                                        uint32_t pos) {
+    if (!mbar_try_wait(bar, parity)) ev_wait_slow(bar, parity, s_abort, dbg, code, pos);
+}
+
+__device__ __forceinline__ float max8(const uint32_t *v) {
+    float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+#pragma unroll
+    for (int j = 2; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+    return m;
+}
+__device__ __forceinline__ float max8f(const float (&v)[8]) {
+    float m = fmaxf(v[0], v[1]);
+#pragma unroll
+    for (int j = 2; j < 8; ++j) m = fmaxf(m, v[j]);
+    return m;
+}
+
+// Branch-free conditional append to the row's staging buffer in shared memory (a 32-bit cursor, no global
+// memory descriptor to re-materialise under the predicate): setp + predicated 64-bit store + predicated add.
+__device__ __forceinline__ void append_if_above(uint32_t &saddr, float s, float tau, uint32_t col) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.gt.f32 p, %1, %2;\n\t"
+        "@p st.shared.v2.u32 [%0], {%3, %4};\n\t"
+        "@p add.u32 %0, %0, 8;\n\t"
+        "}"
+        : "+r"(saddr)
+        : "f"(s), "f"(tau), "r"(col), "r"(__float_as_uint(s))
+        : "memory");
+}
+
+__device__ __forceinline__ uint64_t key_of_raw(uint64_t raw) {
+    return make_key(__uint_as_float(static_cast<uint32_t>(raw >> 32)), static_cast<uint32_t>(raw & 0xFFFFFFFFull));
+}
+__device__ __forceinline__ uint64_t raw_of_key(uint64_t key) {
+    return (static_cast<uint64_t>(__float_as_uint(key_score(key))) << 32) | key_index(key);
+}
+
+// In a 256-bin histogram (bins in DESCENDING order of value) find the bin in which the running count from
+// the top reaches `rank1` (1-based) and the count strictly above that bin.
+__device__ __forceinline__ void hist_find(const uint32_t *hist, int lane, int rank1, int &bin, int &above) {
+    uint32_t my[8];
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {          // lane l owns bins 255-8l .. 248-8l
+        my[j] = hist[255 - 8 * lane - j];
+        sum += static_cast<int>(my[j]);
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int excl = incl - sum;
+    const bool has = excl < rank1 && rank1 <= incl;
+    int b = 0, ab = 0;
+    if (has) {
+        int cum = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (b == 0 && cum + static_cast<int>(my[j]) >= rank1) { b = 256 - 8 * lane - j; ab = cum; }   // b stored +1
+            cum += static_cast<int>(my[j]);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    const int src = m ? (__ffs(m) - 1) : 0;
+    bin = __shfl_sync(0xffffffffu, b, src) - 1;
+    above = __shfl_sync(0xffffffffu, ab, src);
+    if (m == 0u) { bin = 0; above = 0; }
+}
+
+// Rank selection over n orderable keys (global or shared memory; 0 = empty slot), executed by a whole warp:
+// returns a 32-bit prefix P (a lower bound of the (r+1)-th largest key's score bits: the 16 bits below the
+// highest bit in which the keys differ are resolved by two 256-bin histogram passes) such that at least r+1
+// keys have score bits >= P whenever n > r.  Cheap replacement for a sort when only a cut is needed.
+template <typename LoadKey>
+__device__ __forceinline__ uint32_t select_prefix(LoadKey key_at, int n, int r, int lane, uint32_t *hist) {
+    uint32_t lo = 0xFFFFFFFFu, mx = 0u;
+    for (int i = lane; i < n; i += 32) {
+        const uint64_t k = key_at(i);
+        if (k != 0ull) {
+            const uint32_t hi = static_cast<uint32_t>(k >> 32);
+            lo = min(lo, hi);
+            mx = max(mx, hi);
+        }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    uint32_t prefix = mx;
+    if (lo < mx) {
+        const int p = 31 - __clz(lo ^ mx);                 // highest differing bit
+        const int s1 = p >= 7 ? p - 7 : 0;
+        const uint32_t common = (s1 + 8 >= 32) ? 0u : ((mx >> (s1 + 8)) << (s1 + 8));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0u;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            const uint64_t k = key_at(i);
+            if (k != 0ull) atomicAdd(&hist[(static_cast<uint32_t>(k >> 32) >> s1) & 255u], 1u);
+        }
+        __syncwarp();
+        int bin1, above1;
+        hist_find(hist, lane, r + 1, bin1, above1);
+        prefix = common | (static_cast<uint32_t>(bin1) << s1);
+        if (s1 > 0) {
+            const int s2 = s1 >= 8 ? s1 - 8 : 0;
+            const uint32_t sel = (common >> s1) | static_cast<uint32_t>(bin1);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0u;
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                const uint64_t k = key_at(i);
+                const uint32_t hi = static_cast<uint32_t>(k >> 32);
+                if (k != 0ull && (hi >> s1) == sel) atomicAdd(&hist[(hi >> s2) & ((1u << (s1 - s2)) - 1u)], 1u);
+            }
+            __syncwarp();
+            int bin2, above2;
+            hist_find(hist, lane, r + 1 - above1, bin2, above2);
+            prefix |= static_cast<uint32_t>(bin2) << s2;
+        }
+        __syncwarp();
+    }
+    return prefix;
+}
+
+// Overflow protection inside the MMA kernel (rare: a list only gets near its capacity when the starting
+// threshold was far too low): keep the entries of one row's list whose score reaches the (r+1)-th largest.
+__device__ __forceinline__ void compact_list(uint64_t *row_buf, int n, int r, int lane, uint32_t *hist, int &new_cnt,
+                                             float &new_tau) {
+    const uint32_t prefix = select_prefix([&](int i) { return key_of_raw(row_buf[i]); }, n, r, lane, hist);
+    // stable in-place compaction, 32 entries per step (reads of a step complete before its writes)
+    int kept = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const uint64_t raw = (i < n) ? row_buf[i] : 0ull;
+        const bool keep = i < n && static_cast<uint32_t>(key_of_raw(raw) >> 32) >= prefix;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) row_buf[kept + __popc(m & ((1u << lane) - 1u))] = raw;
+        kept += __popc(m);
+        __syncwarp();
+    }
+    new_cnt = kept;
+    new_tau = score_of_bits(prefix);
+}
+
+// Rare paths of the epilogue, kept out of line so that the tile loop stays small.
+// (1) Move every lane's staged entries to the end of its global list; returns the new list length.
+__device__ __forceinline__ int flush_staged(uint32_t sbase, uint32_t saddr, uint64_t *row_buf, int g_cnt) {
+    const int n = static_cast<int>((saddr - sbase) >> 3);
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        uint64_t e;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(e) : "r"(sbase + 8u * static_cast<uint32_t>(i)) : "memory");
+        row_buf[g_cnt + i] = e;
+    }
+    return g_cnt + n;
+}
+// (2) A list within a tile of its capacity (the starting threshold was far too low) is cut to its r_keep best at
+// once.  Returns the new length in the low half and the new threshold's bits in the high half; length 0xFFFF =
+// give up (a huge run of exact ties).  `hist` may alias the warp's (just flushed) staging buffers.
+__device__ __forceinline__ uint64_t overflow_compact(uint64_t *row_buf, int g_cnt, int r_keep, float tau, int lane, uint32_t *hist) {
+    unsigned need = __ballot_sync(0xffffffffu, g_cnt > EV_TRIGGER);
+    uint32_t out_cnt = static_cast<uint32_t>(g_cnt);
+    float out_tau = tau;
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int n_src = __shfl_sync(0xffffffffu, g_cnt, src);
+        const int r_src = __shfl_sync(0xffffffffu, r_keep, src);
+        const uint64_t buf_bits = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(row_buf), src);
+        int nc;
+        float nt;
+        __syncwarp();                                    // the flushed entries are visible to the whole warp
+        compact_list(reinterpret_cast<uint64_t *>(buf_bits), n_src, r_src, lane, hist, nc, nt);
+        if (lane == src) {
+            out_cnt = nc > EV_TRIGGER ? 0xFFFFu : static_cast<uint32_t>(nc);
+            out_tau = nt;
+        }
+    }
+    return (static_cast<uint64_t>(__float_as_uint(out_tau)) << 32) | out_cnt;
+}
+
+template <bool SEED>
+__global__ void __launch_bounds__(EV_THREADS, 1)
+tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
+    extern __shared__ __align__(1024) unsigned char ev_smem[];
+    unsigned char *ring = ev_smem;
+    unsigned char *stg_all = ev_smem + EV_STAGES * EV_STAGE_BYTES;     // [16 warps][32 lanes][EV_STG] staged entries
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stg_all + EV_EPI_WARPS * 32 * EV_STG_BYTES);
+    uint64_t *full_bar = bars;                              // [EV_STAGES] item slab landed
+    uint64_t *empty_bar = bars + EV_STAGES;                 // [EV_STAGES] both issuers' MMAs on the slab retired
+    // Accumulator slot s is used alternately by the two row blocks of one parity (0/2 share the even slots, 1/3
+    // the odd ones).  A warp may run up to three tiles ahead of a slower warp of its row block, i.e. be waiting
+    // for its row block's NEXT use of a slot while the other row block's use in between has not happened yet; a
+    // single parity bit per slot cannot tell those apart (the wait would pass on the stale phase).  Hence one
+    // full/empty barrier pair per (slot, row-block half): phases then advance once per use BY THAT ROW BLOCK.
+    uint64_t *tfull_bar = bars + 2 * EV_STAGES;             // [EV_SLOTS][2]  accumulator slot complete (for row block rb: index 2*s + (rb >> 1))
+    uint64_t *tempty_bar = tfull_bar + 2 * EV_SLOTS;        // [EV_SLOTS][2]  the four warps of that row block have read it
+    uint64_t *afull_bar = tempty_bar + 2 * EV_SLOTS;        // [EV_RB]        A rows of the unit are in tensor memory
+    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + EV_NUM_BARS);
+    volatile uint32_t *s_abort = tmem_base_smem + 1;
+    volatile uint32_t *s_trace = s_abort + 1;          // [20] (debug builds)
+    (void)s_trace;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        *s_abort = 0u;
+        for (int s = 0; s < EV_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 2);
+        }
+        for (int s = 0; s < 2 * EV_SLOTS; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 4);
+        }
+        for (int s = 0; s < EV_RB; ++s) mbar_init(&afull_bar[s], 4);
+        mbar_fence_init();
+    }
+    if (warp == EV_MMA_WARP0) tmem_alloc(tmem_base_smem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+    const int n_units = a.n_row_tiles * a.n_slices;
+    // 640 threads get 96 registers each at launch; the role warpgroup hands 64 of them per thread to the epilogue
+    // warpgroups, whose 64 scores + 8 group maxima + row state do not fit in 96 without spilling in the tile loop
+    // (each role branch starts with its own setmaxnreg: ptxas budgets registers per control-flow region)
+    if (warp >= EV_EPI_WARPS) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(EV_REGS_ROLE));
+      if (warp == EV_TMA_WARP) {
+        // ================= TMA producer: one 64-item x 64-element fp16 slab per tile =================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int sl = unit % a.n_slices;
+            const int t_lo = sl * a.tiles_per_slice;
+            const int t_hi = min(t_lo + a.tiles_per_slice, a.n_col_tiles);
+            const int n_t = SEED ? a.n_seed_tiles : (t_hi - t_lo);
+            for (int i = 0; i < n_t; ++i) {
+                const int t = SEED ? (a.seed_off + i * a.seed_stride) : (t_lo + i);
+                EV_TRACE(0x61, i);
+                ev_wait(&empty_bar[stage], phase ^ 1u, s_abort, a.dbg, 0x100u | stage, static_cast<uint32_t>(i));
+                __syncwarp();
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full_bar[stage], EV_STAGE_BYTES);
+                    tma_load_2d(ring + stage * EV_STAGE_BYTES, &map_b, 0, t * EV_BN, &full_bar[stage]);
+                }
+                __syncwarp();
+                if (++stage == EV_STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+      } else if (warp == EV_MMA_WARP0 || warp == EV_MMA_WARP0 + 1) {
+        // ================= MMA issuers: warp `me` owns row blocks 2*me and 2*me+1 =================
+        const int me = warp - EV_MMA_WARP0;
+        int stage = 0;
+        uint32_t phase = 0, uphase = 0;
+        // Use (g, rb) -- g = tiles issued by this CTA so far -- takes slot (4g + rb) % 6; row block rb comes back to
+        // the same slot every third tile, so its barrier phase for tile g is g / 3.  The slot's previous user is
+        // row block rb ^ 2 at tile g - 2 (rb < 2) or g - 1 (rb >= 2).
+        int g = 0;
+        const int rb0 = 2 * me, rb1 = 2 * me + 1;
+        const int half = me;                                 // rb >> 1 of both row blocks of this warp
+        const int back = me == 0 ? 2 : 1;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int sl = unit % a.n_slices;
+            const int t_lo = sl * a.tiles_per_slice;
+            const int t_hi = min(t_lo + a.tiles_per_slice, a.n_col_tiles);
+            const int n_t = SEED ? a.n_seed_tiles : (t_hi - t_lo);
+            ev_wait(&afull_bar[rb0], uphase, s_abort, a.dbg, 0x200u | rb0, static_cast<uint32_t>(unit));
+            ev_wait(&afull_bar[rb1], uphase, s_abort, a.dbg, 0x200u | rb1, static_cast<uint32_t>(unit));
+            uphase ^= 1u;
+            for (int i = 0; i < n_t; ++i, ++g) {
+                const int slot0 = (4 * g + rb0) % EV_SLOTS, slot1 = (4 * g + rb1) % EV_SLOTS;
+                EV_TRACE(0x51, i);
+                if (g >= back) {
+                    const uint32_t par_prev = static_cast<uint32_t>(((g - back) / 3) & 1);
+                    ev_wait(&tempty_bar[2 * slot0 + (half ^ 1)], par_prev, s_abort, a.dbg, 0x300u | (me << 4) | slot0, static_cast<uint32_t>(i));
+                    ev_wait(&tempty_bar[2 * slot1 + (half ^ 1)], par_prev, s_abort, a.dbg, 0x300u | (me << 4) | slot1, static_cast<uint32_t>(i));
+                }
+                EV_TRACE(0x52, i);
+                ev_wait(&full_bar[stage], phase, s_abort, a.dbg, 0x400u | (me << 4) | stage, static_cast<uint32_t>(i));
+                EV_TRACE(0x53, i);
+                tc_fence_after();
+                __syncwarp();
+                if (elect_one()) {
+                    const uint64_t db = smem_desc_sw128(ring + stage * EV_STAGE_BYTES);
+                    const uint32_t d0 = tmem_base + EV_ACC0 + slot0 * EV_BN;
+                    const uint32_t d1 = tmem_base + EV_ACC0 + slot1 * EV_BN;
+                    const uint32_t a0 = tmem_base + rb0 * 32, a1 = a0 + 32;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ts(d0, a0 + 8 * k, db + 2 * k, EV_IDESC, k > 0 ? 1u : 0u);
+                    umma_commit(&tfull_bar[2 * slot0 + half]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ts(d1, a1 + 8 * k, db + 2 * k, EV_IDESC, k > 0 ? 1u : 0u);
+                    umma_commit(&tfull_bar[2 * slot1 + half]);
+                    umma_commit(&empty_bar[stage]);
+                }
+                __syncwarp();
+                EV_TRACE(0x54, i);
+                if (++stage == EV_STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EV_REGS_EPI));
+        // ================= epilogue: one thread per user row =================
+        const int rb = warp >> 2;                // 128-row block of the unit
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int row_local = rb * 128 + q * 32 + lane;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        // the warp's staging area doubles as the histogram of the (rare) overflow compaction
+        uint32_t *hist = reinterpret_cast<uint32_t *>(stg_all + warp * 32 * EV_STG_BYTES);
+        const uint32_t sbase = smem_u32(stg_all + (warp * 32 + lane) * EV_STG_BYTES);
+        // this row block's slot sequence has period 3 in the tile count: (rb + 4k) % 6, k = g % 3; phase = g / 3
+        const int half = rb >> 1;
+        int slot = rb;
+        int k3 = 0;
+        uint32_t spar = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int rt = unit / a.n_slices, sl = unit % a.n_slices;
+            const int t_lo = sl * a.tiles_per_slice;
+            const int t_hi = min(t_lo + a.tiles_per_slice, a.n_col_tiles);
+            const int n_t = SEED ? a.n_seed_tiles : (t_hi - t_lo);
+            const int64_t row = static_cast<int64_t>(rt) * EV_BM + row_local;
+            const bool row_ok = row < a.Ma;
+            // ---- this thread's user row -> tensor memory (columns 32*rb .. 32*rb+31 of its lane).  Every MMA of
+            // the previous unit that read these columns has retired: this warp has seen the accumulator of the
+            // unit's last tile of its row block, and a commit covers all MMAs issued before it.
+            {
+                uint32_t av[32];
+                if (row_ok) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(a.a16 + row * EV_KPAD);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 x = src[j];
+                        av[4 * j] = x.x; av[4 * j + 1] = x.y; av[4 * j + 2] = x.z; av[4 * j + 3] = x.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) av[j] = 0u;
+                }
+                tmem_st32(lane_base + rb * 32, av);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&afull_bar[rb]);
+            }
+            // ---- per-row state
+            float tk[EV_SEEDK];                               // seed mode: largest tile maxima, descending
+            float tau = INFINITY;
+            bool give_up = false;
+            int r_keep = 0, g_cnt = 0;                        // g_cnt: entries already in the global list
+            uint32_t saddr = sbase;                           // staging cursor
+            uint64_t *row_buf = nullptr;
+            if (SEED) {
+#pragma unroll
+                for (int s = 0; s < EV_SEEDK; ++s) tk[s] = -INFINITY;
+            } else {
+                r_keep = a.kp + (a.exclude_self ? 1 : 0);
+                if (row_ok && a.mask_rowptr != nullptr) {
+                    const int64_t len = a.mask_rowptr[row + 1] - a.mask_rowptr[row];
+                    r_keep += (len < EV_CAP) ? static_cast<int>(len) : EV_CAP;
+                }
+                // a row whose kept set leaves no room for a tile of appends (a user with hundreds of train
+                // items) is not pre-filtered at all: it goes to the exact engine
+                give_up = !row_ok || (r_keep + 32 > EV_TRIGGER);
+                // Any starting threshold is safe: "every unlisted column scored <= the threshold in force when
+                // it was seen" holds either way, and a row left with too few candidates fails certification.
+                if (!give_up) tau = a.tau0 ? a.tau0[row] : -INFINITY;
+                row_buf = a.lists + (static_cast<size_t>(row_ok ? row : 0) * a.n_slices + sl) * EV_CAP;
+            }
+            for (int i = 0; i < n_t; ++i) {
+                const int t = SEED ? (a.seed_off + i * a.seed_stride) : (t_lo + i);
+                EV_TRACE(1, i);
+                ev_wait(&tfull_bar[2 * slot + half], spar, s_abort, a.dbg, 0x500u | (warp << 4) | slot, static_cast<uint32_t>(i));
+                tc_fence_after();
+                const uint32_t taddr = lane_base + EV_ACC0 + slot * EV_BN;
+                uint32_t va[32], vb[32];
+                __syncwarp();
+                EV_TRACE(2, i);
+                tmem_ld32(taddr, va);
+                tmem_ld32(taddr + 32, vb);
+                tmem_ld_wait();
+                // the 64 scores are in registers: hand the slot back BEFORE filtering
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[2 * slot + half]);
+                slot += 4;
+                if (slot >= EV_SLOTS) slot -= EV_SLOTS;
+                if (++k3 == 3) { k3 = 0; spar ^= 1u; }
+                const uint32_t tcol = static_cast<uint32_t>(t) * EV_BN;
+                if (t == a.n_col_tiles - 1 && (a.Nb & (EV_BN - 1)) != 0) {
+                    // zero padding beyond Nb exists in the last column tile only
+                    const uint32_t nb32 = static_cast<uint32_t>(a.Nb);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (tcol + j >= nb32) va[j] = 0xFF800000u;        // -inf
+                        if (tcol + 32 + j >= nb32) vb[j] = 0xFF800000u;
+                    }
+                }
+                EV_TRACE(3, i);
+                float m8[8];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    m8[g] = max8(va + 8 * g);
+                    m8[4 + g] = max8(vb + 8 * g);
+                }
+                const float mh0 = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+                const float mh1 = fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]));
+                const float top = fmaxf(mh0, mh1);
+                if (SEED) {
+                    float x = top;
+#pragma unroll
+                    for (int s = 0; s < EV_SEEDK; ++s) {
+                        const float hi = fmaxf(tk[s], x);
+                        x = fminf(tk[s], x);
+                        tk[s] = hi;
+                    }
+                } else if (__any_sync(0xffffffffu, top > tau)) {
+                    // some row of the warp has a candidate in this tile: narrow down to 32-column halves, then to
+                    // 8-column groups, and only there look at single columns
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (!__any_sync(0xffffffffu, (h ? mh1 : mh0) > tau)) continue;
+#pragma unroll
+                        for (int gg = 0; gg < 4; ++gg) {
+                            const int g = 4 * h + gg;
+                            if (!__any_sync(0xffffffffu, m8[g] > tau)) continue;
+                            EV_TRACE(4 + g, i);
+                            if (__any_sync(0xffffffffu, saddr - sbase > static_cast<uint32_t>(EV_STG_LIMIT))) {
+                                EV_TRACE(0x20 + g, i);
+                                g_cnt = flush_staged(sbase, saddr, row_buf, g_cnt);
+                                saddr = sbase;
+                            }
+                            const uint32_t *v = h ? (vb + 8 * gg) : (va + 8 * gg);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) append_if_above(saddr, __uint_as_float(v[j]), tau, tcol + 8 * g + j);
+                        }
+                    }
+                    // A list that gets within a tile of its capacity is cut to its r_keep best.  (Checked once per
+                    // tile: a tile adds at most 64 entries, so a list below the trigger cannot overflow inside it.)
+                    EV_TRACE(0x30, i);
+                    if (__any_sync(0xffffffffu, g_cnt + static_cast<int>((saddr - sbase) >> 3) > EV_TRIGGER)) {
+                        EV_TRACE(0x31, i);
+                        g_cnt = flush_staged(sbase, saddr, row_buf, g_cnt);
+                        saddr = sbase;
+                        __syncwarp();
+                        const uint64_t r = overflow_compact(row_buf, g_cnt, r_keep, tau, lane, hist);
+                        g_cnt = static_cast<int>(r & 0xFFFFu);
+                        tau = __uint_as_float(static_cast<uint32_t>(r >> 32));
+                        if (g_cnt == 0xFFFF) { give_up = true; tau = INFINITY; g_cnt = 0; }
+                        __syncwarp();                             // the histogram space is staging space again
+                        EV_TRACE(0x32, i);
+                    }
+                }
+                EV_TRACE(0x40, i);
+            }
+            // ---- end of unit
+            if (SEED) {
+                float v = tk[0];
+#pragma unroll
+                for (int s = 1; s < EV_SEEDK; ++s)
+                    if (s < a.seed_k) v = tk[s];
+                if (row_ok) a.tau0[row] = v;
+            } else {
+                g_cnt = flush_staged(sbase, saddr, row_buf, g_cnt);
+                if (__any_sync(0xffffffffu, g_cnt > EV_CAP)) {}      // (cannot happen: flushes keep lists below the trigger + staging)
+                if (row_ok) {
+                    const size_t o = static_cast<size_t>(row) * a.n_slices + sl;
+                    a.cnt_out[o] = give_up ? 0 : g_cnt;
+                    a.tau_out[o] = give_up ? INFINITY : tau;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == EV_MMA_WARP0) tmem_dealloc(tmem_base, 512);
+}
+
+constexpr size_t ev_smem_bytes() {
+    return static_cast<size_t>(EV_STAGES) * EV_STAGE_BYTES + static_cast<size_t>(EV_EPI_WARPS) * 32 * EV_STG_BYTES + EV_NUM_BARS * 8 + 64 + 128;
+}
+
+// ---- fp32 -> scaled fp16 operand copies -----------------------------------------------------------------
+// x' = x * 2^-e is exact; fp16(x') has relative error <= 2^-11 in the normal range and absolute error <= 2^-25
+// below 2^-14.  A rows get their own exponent (a positive per-row factor does not change the row's ranking);
+// the item table shares one exponent.  16 lanes per row, float4 each: rows of up to 64 elements.
+__global__ void absmax_kernel(const float *__restrict__ x, int64_t n, unsigned int *__restrict__ out_bits) {
+    float m = 0.0f;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));   // non-negative floats order as integers
+}
+
+__device__ __forceinline__ int scale_exponent(float amax) {
+    // e with amax * 2^-e in [1, 2) (0 for an all-zero input); clamped so that 2^-e and 2^e are normal floats
+    if (!(amax > 0.0f)) return 0;
+    int e = static_cast<int>((__float_as_uint(amax) >> 23) & 0xFFu) - 127;
+    if (e < -100) e = -100;
+    if (e > 100) e = 100;
+    return e;
+}
+__device__ __forceinline__ float pow2f(int e) { return __uint_as_float(static_cast<uint32_t>(127 + e) << 23); }
+
+// per_row != 0: each row uses its own exponent; else the exponent of *shared_absmax_bits.
+// stats (nullable, shared mode): [0] = 2^e as a float, [1] = max scaled row norm (upper bound) via atomicMax.
+__global__ void to_f16_scaled_kernel(const float *__restrict__ x, int64_t n_rows, int D, int per_row,
+                                     const unsigned int *__restrict__ shared_absmax_bits, __half *__restrict__ out,
+                                     float *__restrict__ row_norm_scaled, float *__restrict__ row_scale,
+                                     float *__restrict__ stats) {
+    const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4;
+    const int sub = threadIdx.x & 15;
+    const bool ok = row < n_rows;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok && sub * 4 < D) v = *reinterpret_cast<const float4 *>(x + row * D + sub * 4);
+    float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    const int e = per_row ? scale_exponent(amax) : scale_exponent(__uint_as_float(*shared_absmax_bits));
+    const float sc = pow2f(-e);
+    if (ok) {
+        const __half2 lo = __floats2half2_rn(v.x * sc, v.y * sc), hi = __floats2half2_rn(v.z * sc, v.w * sc);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+        *reinterpret_cast<uint2 *>(out + row * EV_KPAD + sub * 4) = pk;
+    }
+    // fp32 summation error <= D * 2^-24 relative: rounded up, the norm feeds an upper bound
+    const float nrm = sqrtf(ss) * sc * (1.0f + 2.0e-7f * static_cast<float>(D));
+    if (ok && sub == 0) {
+        if (row_norm_scaled) row_norm_scaled[row] = nrm;
+        if (row_scale) row_scale[row] = pow2f(e);
+        if (stats) {
+            atomicMax(reinterpret_cast<unsigned int *>(stats + 1), __float_as_uint(nrm));
+            if (row == 0) stats[0] = pow2f(e);
+        }
+    }
+}
+
+// ---- list post-processing + exact re-score + certification: one warp per row ------------------------------
+struct RescoreArgs {
+    const float *A;            // fp32 operands (canonical arithmetic)
+    const float *B;
+    int64_t Ma, Nb;
+    int D, K, n_slices, kp;
+    const uint64_t *lists;     // [Ma][n_slices][EV_CAP]
+    const int32_t *cnt;        // [Ma][n_slices]
+    const float *tau;          // [Ma][n_slices]
+    const float *a_norm;       // [Ma] scaled row norms (upper bounds)
+    const float *a_scale;      // [Ma] 2^ea
+    const float *b_stats;      // [0] 2^eb, [1] max scaled item norm (upper bound)
+    float gamma;               // |approx - canonical| <= gamma * |a'| * |b'|max in scaled units
+    const int64_t *mask_rowptr;
+    const int32_t *mask_col;
+    float mask_value;
+    int exclude_self;
+    int64_t self_off;
+    int64_t id_offset;
+    int64_t *out_idx;
+    float *out_score;
+    int32_t *fallback_rows;    // rows whose exact top-K could not be certified
+    uint64_t *fallback_seeds;  // their exact K-th best key so far (0 if fewer than K entries)
+    unsigned int *fallback_count;
+    const unsigned int *abort_flag;   // != 0: the pre-filter pipeline timed out -> every row goes to the exact engine
+};
+
+constexpr int kRescoreWarps = 4;
+
+__global__ void __launch_bounds__(kRescoreWarps * 32) rescore_lists_kernel(const RescoreArgs a, const int keys_per_warp) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];   // [warps][keys_per_warp] keys, then [warps][256] histogram
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * kRescoreWarps + wib;
+    if (row >= a.Ma) return;
+    uint64_t *keys = reinterpret_cast<uint64_t *>(rs_smem) + static_cast<size_t>(wib) * keys_per_warp;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(reinterpret_cast<uint64_t *>(rs_smem) + static_cast<size_t>(kRescoreWarps) * keys_per_warp) + wib * 256;
+    // ---- gather the row's lists (all column slices)
+    int n = 0;
+    float tmain = -INFINITY;        // every valid column outside `keys` has approximate score <= tmain
+    bool bad = *a.abort_flag != 0u;
+    for (int s = 0; s < a.n_slices; ++s) {
+        const size_t o = static_cast<size_t>(row) * a.n_slices + s;
+        const int c = a.cnt[o];
+        const float t = a.tau[o];
+        if (!(t < INFINITY)) bad = true;
+        tmain = fmaxf(tmain, t);
+        const uint64_t *src = a.lists + o * EV_CAP;
+        for (int i = lane; i < c; i += 32) keys[n + i] = key_of_raw(src[i]);
+        n += c;
+    }
+    int64_t m_lo = 0;
+    int nm_all = 0;
+    if (a.mask_rowptr != nullptr) {
+        m_lo = a.mask_rowptr[row];
+        nm_all = static_cast<int>(a.mask_rowptr[row + 1] - m_lo);
+    }
+    uint64_t kth = 0ull;
+    bool ok = false;
+    if (!bad) {
+        __syncwarp();
+        // ---- cut to the r_keep best by approximate score (no sort), then drop invalid columns
+        const int r_keep = a.kp + (a.exclude_self ? 1 : 0) + (nm_all < EV_CAP ? nm_all : EV_CAP);
+        uint32_t prefix = 0u;
+        if (n > 64 && n > r_keep + 1) {
+            prefix = select_prefix([&](int i) { return keys[i]; }, n, r_keep, lane, hist);
+            tmain = fmaxf(tmain, score_of_bits(prefix));     // everything cut scored below the prefix
+        }
+        const int64_t self_col = a.exclude_self ? row + a.self_off : -1;
+        int m = 0;                                            // valid keys, compacted to keys[0..m)
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const uint64_t key = (i < n) ? keys[i] : 0ull;
+            bool v = key != 0ull && static_cast<uint32_t>(key >> 32) >= prefix;
+            if (v) {
+                const int64_t col = key_index(key);
+                if (col == self_col) v = false;
+                int lo = 0, hi = nm_all;                      // binary search in the row's sorted train items
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int32_t mc = a.mask_col[m_lo + mid];
+                    if (mc < col) lo = mid + 1; else hi = mid;
+                }
+                if (lo < nm_all && a.mask_col[m_lo + lo] == col) v = false;
+            }
+            const unsigned bm = __ballot_sync(0xffffffffu, v);
+            __syncwarp();
+            if (v) keys[m + __popc(bm & ((1u << lane) - 1u))] = key;
+            m += __popc(bm);
+            __syncwarp();
+        }
+        int P = 64;
+        while (P < m) P <<= 1;
+        for (int t = m + lane; t < P; t += 32) keys[t] = 0ull;
+        __syncwarp();
+        warp_sort_desc(keys, P, lane);
+        int n_cand = m;
+        if (m > a.kp) {                                       // only the kp best valid candidates are re-scored
+            tmain = fmaxf(tmain, key_score(keys[a.kp]));
+            n_cand = a.kp;
+        }
+        // ---- exact canonical scores of the candidates
+        const float *ar = a.A + row * a.D;
+        uint64_t mine[EV_KP_MAX / 32];
+#pragma unroll
+        for (int r = 0; r < EV_KP_MAX / 32; ++r) {
+            const int t = lane + r * 32;
+            mine[r] = (t < n_cand) ? keys[t] : 0ull;
+        }
+        __syncwarp();
+        int nm = nm_all < a.K ? nm_all : a.K;
+        int P2 = 64;
+        while (P2 < n_cand + nm) P2 <<= 1;
+#pragma unroll 1
+        for (int r = 0; r < EV_KP_MAX / 32; ++r) {
+            const int t = lane + r * 32;
+            if (t >= n_cand) continue;
+            const uint32_t col = key_index(mine[r]);
+            const float *br = a.B + static_cast<int64_t>(col) * a.D;
+            float acc = 0.0f;
+            int k = 0;
+            // canonical chain: k ascending, one fmaf per term
+            for (; k + 32 <= a.D; k += 32) {
+                float4 y[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) y[u] = __ldg(reinterpret_cast<const float4 *>(br + k) + u);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 x = *reinterpret_cast<const float4 *>(ar + k + 4 * u);
+                    acc = fmaf(x.x, y[u].x, acc);
+                    acc = fmaf(x.y, y[u].y, acc);
+                    acc = fmaf(x.z, y[u].z, acc);
+                    acc = fmaf(x.w, y[u].w, acc);
+                }
+            }
+            for (; k < a.D; k += 4) {
+                const float4 x = *reinterpret_cast<const float4 *>(ar + k);
+                const float4 y = __ldg(reinterpret_cast<const float4 *>(br + k));
+                acc = fmaf(x.x, y.x, acc);
+                acc = fmaf(x.y, y.y, acc);
+                acc = fmaf(x.z, y.z, acc);
+                acc = fmaf(x.w, y.w, acc);
+            }
+            keys[t] = make_key(acc, col);
+        }
+        // the first K train items re-enter with mask_value (Model/LightGCN.py:150-152)
+        for (int t = n_cand + lane; t < P2; t += 32) {
+            uint64_t key = 0ull;
+            if (t < n_cand + nm) {
+                const int32_t mc = a.mask_col[m_lo + (t - n_cand)];
+                if (mc >= 0 && mc < a.Nb) key = make_key(a.mask_value, static_cast<uint32_t>(mc));
+            }
+            keys[t] = key;
+        }
+        __syncwarp();
+        warp_sort_desc(keys, P2, lane);
+        // ---- certification: a valid column outside the candidate set has approximate (scaled) score <= tmain,
+        // hence canonical score <= (tmain + eps') * 2^(ea+eb); the exact top-K is final iff its K-th score is
+        // strictly above that.  (The power-of-two factors are exact; eps' is rounded up.)
+        kth = keys[a.K - 1];
+        const float eps = a.gamma * a.a_norm[row] * a.b_stats[1];
+        const float bound = (tmain + eps * 1.0001f) * (a.a_scale[row] * a.b_stats[0]);
+        const bool complete = (tmain == -INFINITY);
+        ok = kth != 0ull && (complete || key_score(kth) > bound);
+    }
+    if (ok) {
+        for (int t = lane; t < a.K; t += 32) {
+            const uint64_t key = keys[t];
+            a.out_idx[row * a.K + t] = static_cast<int64_t>(key_index(key)) + a.id_offset;
+            if (a.out_score) a.out_score[row * a.K + t] = key_score(key);
+        }
+    } else if (lane == 0) {
+        const unsigned slot = atomicAdd(a.fallback_count, 1u);
+        a.fallback_rows[slot] = static_cast<int32_t>(row);
+        a.fallback_seeds[slot] = kth;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn ev_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+bool make_map_f16(CUtensorMap *map, const void *base, int64_t rows) {
+    EncodeTiledFn fn = ev_encode_fn();
+    if (!fn) return false;
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(EV_KPAD), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(EV_KPAD) * 2};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(EV_KPAD), static_cast<cuuint32_t>(EV_BN)};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t al256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
+
+// Smallest k with P(Poisson(x) >= k) <= p.
+int poisson_rank(double x, double p) {
+    double term = exp(-x), cdf = term;      // P(Poisson <= 0)
+    int k = 1;
+    while (1.0 - cdf > p && k < 64) { term *= x / k; cdf += term; ++k; }
+    return k;
+}
+
+}  // namespace
+
+// Column slices only buy load balance: all slices of a row share the row's starting threshold, so a slice's list
+// holds its share of the row's candidates.  Estimated time ~ rounds(units / SMs) / slices, plus 2 % per extra
+// slice for the additional unit start-ups and list bookkeeping.
+int tc_eval_choose_slices(int64_t Ma, int64_t Nb) {
+    const int row_tiles = static_cast<int>((Ma + EV_BM - 1) / EV_BM);
+    const int col_tiles = static_cast<int>((Nb + EV_BN - 1) / EV_BN);
+    const int sms = sm_count();
+    int slices = 1;
+    double best = 1e30;
+    for (int s = 1; s <= 4; ++s) {
+        if (s > 1 && col_tiles / s < 64) break;
+        const int rounds = (row_tiles * s + sms - 1) / sms;
+        const double cost = static_cast<double>(rounds) / s * (1.0 + 0.02 * (s - 1));
+        if (cost < best - 1e-9) { best = cost; slices = s; }
+    }
+    return slices;
+}
+
+size_t tc_eval_workspace_bytes(int64_t Ma, int64_t Nb, int D) {
+    const int slices = tc_eval_choose_slices(Ma, Nb);
+    size_t n = 256;                                                    // counters
+    n += al256(static_cast<size_t>(Ma) * EV_KPAD * 2);                  // A fp16
+    n += al256(static_cast<size_t>(Nb) * EV_KPAD * 2);                  // B fp16
+    n += 2 * al256(static_cast<size_t>(Ma) * 4) + 256;                  // A norms and scales, B stats
+    n += al256(static_cast<size_t>(Ma) * 4);                            // starting thresholds
+    n += 2048 + al256(static_cast<size_t>(Ma) * slices * EV_CAP * 8);   // candidate lists (2 KB aligned)
+    n += 2 * al256(static_cast<size_t>(Ma) * slices * 4);               // list lengths, final thresholds
+    n += al256(static_cast<size_t>(Ma) * 4);                            // fallback row list
+    n += al256(static_cast<size_t>(Ma) * 8);                            // ... and their seed keys
+    n += rank_listed_workspace_bytes(D);                                // exact engine for uncertified rows
+    return n;
+}
+
+bool tc_eval_supported(int64_t Ma, int64_t Nb, int D, int K) {
+    // small item tables stay on the exact engine (nothing to win, and K' must be well below Nb)
+    return D % 4 == 0 && D >= 4 && D <= EV_KPAD && K >= 1 && K <= 64 && Nb >= 2048 && Ma >= 1 && Ma < 0x7FFFFFF0LL &&
+           Nb < 0x7FFFFFC0LL && ev_encode_fn() != nullptr;
+}
+
+// A, B: fp32 operands (same pointer allowed).  Computes the exact canonical top-K of every row of A.
+int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes, cudaStream_t stm) {
+    if (workspace_bytes < tc_eval_workspace_bytes(e.Ma, e.Nb, e.d)) return CHAOREC_E_WORKSPACE;
+    const int slices = tc_eval_choose_slices(e.Ma, e.Nb);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    unsigned int *counters = reinterpret_cast<unsigned int *>(ws); ws += 256;
+    __half *a16 = reinterpret_cast<__half *>(ws); ws += al256(static_cast<size_t>(e.Ma) * EV_KPAD * 2);
+    __half *b16 = reinterpret_cast<__half *>(ws); ws += al256(static_cast<size_t>(e.Nb) * EV_KPAD * 2);
+    float *a_norm = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
+    float *a_scale = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
+    float *b_stats = reinterpret_cast<float *>(ws); ws += 256;
+    float *tau0 = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
+    ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ws) + 2047) & ~static_cast<uintptr_t>(2047));
+    uint64_t *lists = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * EV_CAP * 8);
+    int32_t *cnt = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * 4);
+    float *tau = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * 4);
+    int32_t *fb_rows = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
+    uint64_t *fb_seeds = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 8);
+    void *rank_ws = ws;
+    const size_t rank_ws_bytes = workspace_bytes - static_cast<size_t>(ws - static_cast<unsigned char *>(workspace));
+
+    // counters[16] = fallback count (read by the host shim), counters[32] = max |B| bits; b_stats zeroed for atomicMax
+    if (cudaMemsetAsync(counters, 0, 256, stm) != cudaSuccess || cudaMemsetAsync(b_stats, 0, 256, stm) != cudaSuccess) {
+        cudaGetLastError();
+        return CHAOREC_E_LAUNCH;
+    }
+    {
+        const int64_t nb_el = e.Nb * e.d;
+        int64_t blocks = (nb_el + 256 * 8 - 1) / (256 * 8);
+        if (blocks > 4096) blocks = 4096;
+        absmax_kernel<<<static_cast<unsigned>(blocks), 256, 0, stm>>>(e.B, nb_el, counters + 32);
+        to_f16_scaled_kernel<<<static_cast<unsigned>((e.Ma * 16 + 255) / 256), 256, 0, stm>>>(e.A, e.Ma, e.d, 1, nullptr, a16, a_norm,
+                                                                                              a_scale, nullptr);
+        to_f16_scaled_kernel<<<static_cast<unsigned>((e.Nb * 16 + 255) / 256), 256, 0, stm>>>(e.B, e.Nb, e.d, 0, counters + 32, b16,
+                                                                                              nullptr, nullptr, b_stats);
+    }
+    CUtensorMap map_b;
+    if (!make_map_f16(&map_b, b16, e.Nb)) return CHAOREC_E_LAUNCH;
+
+    int kp = e.K <= 20 ? 32 : (e.K <= 50 ? 64 : 128);
+    if (e.kp_hint == 32 || e.kp_hint == 64 || e.kp_hint == 128) kp = e.kp_hint;
+    if (const char *env = getenv("CHAOREC_TC_KP")) {
+        const int v = atoi(env);
+        if (v == 32 || v == 64 || v == 128) kp = v;
+    }
+    if (kp < e.K + 8) kp = (e.K + 8 <= 64) ? 64 : 128;
+
+    EvalArgs t{};
+    t.Ma = e.Ma; t.Nb = e.Nb;
+    t.n_row_tiles = static_cast<int>((e.Ma + EV_BM - 1) / EV_BM);
+    t.n_col_tiles = static_cast<int>((e.Nb + EV_BN - 1) / EV_BN);
+    t.n_slices = slices;
+    t.tiles_per_slice = (t.n_col_tiles + slices - 1) / slices;
+    t.a16 = a16;
+    t.mask_rowptr = e.mask_rowptr;
+    t.exclude_self = e.exclude_self;
+    t.kp = kp;
+    t.lists = lists; t.cnt_out = cnt; t.tau_out = tau; t.tau0 = nullptr;
+    t.dbg = counters + 36;
+
+    const size_t smem = ev_smem_bytes();
+    cudaError_t ce = cudaFuncSetAttribute(tc_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(tc_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (ce != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
+
+    // ---- seed pass: starting thresholds from an evenly spaced sample of column tiles ------------------------
+    // The k-th largest sample score sits, in expectation, at rank k / f of the full row (f = sampled fraction);
+    // k is the smallest rank that leaves >= need full-row columns above the threshold with probability
+    // 1 - 1e-3 (a Poisson(need * f) variable reaching k), need = K' + a typical train-item list.  Rows left
+    // short fail certification and go to the exact engine.  The sample is sized so that k <= 16 tile maxima.
+    int seed_tiles = 256;
+    if (const char *env = getenv("CHAOREC_TC_SEED_TILES")) seed_tiles = atoi(env);
+    const double need = kp + 24.0;
+    {
+        const int cap = static_cast<int>(6.0 / need * t.n_col_tiles);       // need * f <= 6  ->  k <= 16
+        if (seed_tiles > cap) seed_tiles = cap;
+        if (seed_tiles > t.n_col_tiles / 2) seed_tiles = t.n_col_tiles / 2;
+    }
+    if (seed_tiles >= 2) {
+        EvalArgs p = t;
+        p.n_slices = 1;
+        p.tiles_per_slice = t.n_col_tiles;
+        p.n_seed_tiles = seed_tiles;
+        p.seed_stride = t.n_col_tiles / seed_tiles;
+        p.seed_off = p.seed_stride / 2;
+        const double f = static_cast<double>(seed_tiles) * EV_BN / static_cast<double>(e.Nb);
+        int k_seed = poisson_rank(need * f, 1e-3);
+        if (k_seed < 2) k_seed = 2;
+        if (k_seed > EV_SEEDK) k_seed = EV_SEEDK;
+        p.seed_k = k_seed;
+        p.tau0 = tau0;
+        const int pgrid = p.n_row_tiles < sm_count() ? p.n_row_tiles : sm_count();
+        tc_eval_kernel<true><<<pgrid, EV_THREADS, smem, stm>>>(map_b, p);
+        t.tau0 = tau0;
+    }
+    {
+        const int n_units = t.n_row_tiles * slices;
+        const int grid = n_units < sm_count() ? n_units : sm_count();
+        tc_eval_kernel<false><<<grid, EV_THREADS, smem, stm>>>(map_b, t);
+    }
+
+    RescoreArgs r{};
+    r.A = e.A; r.B = e.B; r.Ma = e.Ma; r.Nb = e.Nb; r.D = e.d; r.K = e.K; r.n_slices = slices; r.kp = kp;
+    r.lists = lists; r.cnt = cnt; r.tau = tau; r.a_norm = a_norm; r.a_scale = a_scale; r.b_stats = b_stats;
+    // |s~' - s'| <= gamma |a'||b'|max in scaled units, against the CANONICAL fp32 score s':
+    //   fp16 rounding of both operands      2 * 2^-11 + 2^-22
+    //   fp16 subnormal flush (|x'| < 2^-14)  2^-24 * sqrt(64) relative to |a'||b'|max (both >= 1)
+    //   tensor-core fp32 accumulation        <= 2 d 2^-23   (truncation per addition assumed at worst)
+    //   canonical chain's own rounding       <= d 2^-24
+    r.gamma = (9.765625e-4f + 2.4e-7f + 4.8e-7f) + 2.5f * static_cast<float>(e.d) * 1.1920929e-7f;
+    r.mask_rowptr = e.mask_rowptr; r.mask_col = e.mask_col; r.mask_value = e.mask_value;
+    r.exclude_self = e.exclude_self; r.self_off = e.self_off;
+    r.id_offset = e.id_offset; r.out_idx = e.out_idx; r.out_score = e.out_score;
+    r.fallback_rows = fb_rows; r.fallback_seeds = fb_seeds; r.fallback_count = counters + 16;
+    r.abort_flag = counters + 36;
+    {
+        int keys_per_warp = 512;                                   // a power of two >= all listed entries of a row
+        while (keys_per_warp < slices * EV_CAP) keys_per_warp <<= 1;
+        const size_t rs_smem = static_cast<size_t>(kRescoreWarps) * (keys_per_warp * 8 + 256 * 4);
+        ce = cudaFuncSetAttribute(rescore_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rs_smem));
+        if (ce != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
+        rescore_lists_kernel<<<static_cast<unsigned>((e.Ma + kRescoreWarps - 1) / kRescoreWarps), kRescoreWarps * 32, rs_smem, stm>>>(
+            r, keys_per_warp);
+    }
+    int rc = launch_status();
+    if (rc != CHAOREC_OK) return rc;
+    // rows that could not be certified: exact CUDA-core engine over the listed rows only
+    EngineArgs fb = e;
+    fb.row_list = fb_rows;
+    fb.row_count_dev = counters + 16;
+    fb.seed_keys = fb_seeds;
+    return rank_launch_engine(fb, rank_ws, rank_ws_bytes, stm);
+}
+
+}  // namespace chaorec

@@ -94,6 +94,11 @@ def rank_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, mask: Optional[Mas
         tensor = bool(lib.chaorec_uses_tensor_engine(U, I, d, int(topk)))
         stats["engine"] = "tensor" if tensor else "exact"
         stats["fallback_rows"] = int(ws[64:68].view(torch.int32).item()) if tensor else 0
+        # d <= 64 engine: first time-out record of the MMA pipeline's bounded waits (all zero = healthy; a non-zero
+        # flag means every row was recomputed by the exact engine -- correct but slow, see csrc/tc_eval.cu)
+        stats["pipeline_timeout"] = [int(v) for v in ws[144:176].view(torch.int32).tolist()] if tensor and d <= 64 else [0] * 8
+        if stats["pipeline_timeout"][0]:
+            stats["pipeline_trace"] = [hex(int(v) & 0xFFFFFFFF) for v in ws[176:256].view(torch.int32).tolist()]
     return (out_idx, out_score) if return_scores else out_idx
 
 
