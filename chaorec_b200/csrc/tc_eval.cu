@@ -36,41 +36,43 @@ namespace chaorec {
 namespace {
 using namespace ptx;
 
-constexpr int EV_BM = 512;                        // user rows per unit (4 MMA row blocks)
+constexpr int EV_BM = 384;                        // user rows per unit (3 MMA row blocks)
 constexpr int EV_BN = 64;                         // item columns per tile
-constexpr int EV_RB = 4;
+constexpr int EV_RB = 3;
 constexpr int EV_KPAD = 64;                       // inner dimension of the fp16 copies (d zero-padded)
 constexpr int EV_STAGES = 12;                     // item-slab ring
 constexpr int EV_STAGE_BYTES = EV_BN * EV_KPAD * 2;
-constexpr int EV_SLOTS = 6;                       // accumulator slots (128 lanes x 64 columns each)
-constexpr int EV_ACC0 = 128;                      // TMEM columns [0,128) hold A: row block rb at 32*rb
+constexpr int EV_SLOTS = 2 * EV_RB;               // accumulator slots (128 lanes x 64 columns): two private ones per row block
+constexpr int EV_ACC0 = 32 * EV_RB;               // TMEM columns [0,96) hold A: row block rb at 32*rb
 constexpr int EV_CAP = 256;                       // list capacity per (row, slice)
-constexpr int EV_TRIGGER = EV_CAP - 64;           // a tile appends at most 64 entries
-constexpr int EV_EPI_WARPS = 16;
-constexpr int EV_TMA_WARP = 16;
-constexpr int EV_MMA_WARP0 = 17;                  // warps 17, 18 issue the MMAs of row blocks 0-1 / 2-3
-constexpr int EV_THREADS = 20 * 32;              // warp 19 idles: setmaxnreg works on whole warpgroups
-constexpr int EV_REGS_ROLE = 32;                  // registers per thread after setmaxnreg: role warpgroup
-constexpr int EV_REGS_EPI = 112;                  // ... and the four epilogue warpgroups (96 at launch)
-constexpr int EV_SEEDK = 16;                      // tile maxima kept per row in seed mode
-constexpr int EV_STG = 28;                        // entries of a row's shared-memory staging buffer
+constexpr int EV_TRIGGER = EV_CAP - 64;           // (a tile appends at most 32 entries to a list)
+constexpr int EV_CH = 2;                          // epilogue threads per row: each takes 32 of a tile's 64 columns
+constexpr int EV_EPI_WARPS = 4 * EV_RB * EV_CH;   // warp w: row block w / 8, column half (w / 4) % 2, TMEM lane quarter w % 4
+constexpr int EV_TMA_WARP = EV_EPI_WARPS;         // warp 24
+constexpr int EV_MMA_WARP0 = EV_EPI_WARPS + 1;    // warps 25, 26, 27 issue the MMAs of row blocks 0, 1, 2
+constexpr int EV_THREADS = (EV_EPI_WARPS + 1 + EV_RB) * 32;   // 896 threads -> 72 registers each
+constexpr int EV_SEEDK = 20;                      // tile maxima kept per row in seed mode
+constexpr int EV_SEED_TAB = 128;                  // per-row seed rank is looked up by the row's train-item count
+constexpr int EV_STG = 16;                        // entries of a list's shared-memory staging buffer
 constexpr int EV_STG_BYTES = EV_STG * 8;
 constexpr int EV_STG_LIMIT = (EV_STG - 8) * 8;    // flush before a group of 8 appends could overflow it
-constexpr int EV_NUM_BARS = 2 * EV_STAGES + 4 * EV_SLOTS + EV_RB;
+constexpr int EV_NUM_BARS = 2 * EV_STAGES + 2 * EV_SLOTS + EV_RB;
 constexpr uint32_t EV_IDESC = make_idesc_m128(EV_BN, /*f32 acc*/ 1, /*f16 operands*/ 0);
 constexpr int EV_KP_MAX = 128;
 
 struct EvalArgs {
     int64_t Ma, Nb;
     int n_row_tiles, n_slices, tiles_per_slice, n_col_tiles;
-    int n_seed_tiles, seed_stride, seed_off, seed_k;   // seed mode: tile i of a unit = seed_off + i * seed_stride
+    int n_seed_tiles, seed_stride, seed_off;           // seed mode: tile i of a unit = seed_off + i * seed_stride
+    unsigned char seed_k[EV_SEED_TAB];                 // seed rank (1-based, <= EV_SEEDK) by train-item count of the row
     const __half *a16;            // [Ma][64] scaled fp16 rows
     const int64_t *mask_rowptr;   // only the row lengths are used here
     int exclude_self;
     int kp;
-    uint64_t *lists;              // [Ma][n_slices][EV_CAP] raw entries (score bits << 32 | column), 2 KB aligned
-    int32_t *cnt_out;             // [Ma][n_slices]
-    float *tau_out;               // [Ma][n_slices] threshold in force at the end of the unit (+inf: row gave up)
+    uint64_t *lists;              // [Ma][n_slices][EV_CH][EV_CAP] raw entries (score bits << 32 | column), 2 KB aligned
+    int32_t *cnt_out;             // [Ma][n_slices][EV_CH]
+    float *tau_out;               // [Ma][n_slices][EV_CH] threshold in force at the end of the unit (+inf: row gave up)
+    float *seed_scratch;          // seed mode: [gridDim.x][EV_BM][EV_CH][EV_SEEDK] half-tile maxima of the CTA's current unit
     float *tau0;                  // [Ma] starting thresholds: written in seed mode, read in main mode (nullable)
     unsigned int *dbg;            // [0] = pipeline time-out flag, [1..7] = first time-out record (see ev_wait)
 };
@@ -89,14 +91,33 @@ constexpr unsigned long long EV_WAIT_NS = 4000000000ull;   // 4 s
 #else
 #define EV_TRACE(marker, posv) do { } while (0)
 #endif
-__device__ __forceinline__ void ev_wait_slow(uint64_t *bar, uint32_t parity, volatile uint32_t *s_abort, unsigned int *dbg,
-                                          uint32_t code, uint32_t pos) {
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (!mbar_try_wait(bar, parity)) {
+// try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes (or the hint
+// expires) instead of polling through the issue slots of the warps that have work (with plain try_wait the 16
+// epilogue warps spent a quarter of the kernel's instructions polling: profiles/r02_eval_v2a_*).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void ev_wait(uint64_t *bar, uint32_t parity, volatile uint32_t *s_abort, unsigned int *dbg, uint32_t code,
+                                        uint32_t pos) {
+    if (mbar_try_wait_hint(bar, parity, 20000u)) return;
+    uint32_t n = 0;
+    unsigned long long t0 = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if ((++n & 63u) != 0u) continue;                   // look at the clock and the abort flag every 64th retry
         if (*s_abort) return;
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t0 == 0) t0 = t1;
         if (t1 - t0 > EV_WAIT_NS) {
             *s_abort = 1u;
             if (dbg != nullptr && atomicExch(&dbg[0], 1u) == 0u) {
@@ -109,16 +130,12 @@ __device__ __forceinline__ void ev_wait_slow(uint64_t *bar, uint32_t parity, vol
                 dbg[6] = static_cast<unsigned int>(w >> 32);
                 dbg[7] = threadIdx.x;
 #ifdef CHAOREC_EV_TRACE
-                for (int w = 0; w < 20; ++w) dbg[8 + w] = s_abort[1 + w];
+                for (int w2 = 0; w2 < 20; ++w2) dbg[8 + w2] = s_abort[1 + w2];
 #endif
             }
             return;
         }
     }
-}
-__device__ __forceinline__ void ev_wait(uint64_t *bar, uint32_t parity, volatile uint32_t *s_abort, unsigned int *dbg, uint32_t code,
-                                        uint32_t pos) {
-    if (!mbar_try_wait(bar, parity)) ev_wait_slow(bar, parity, s_abort, dbg, code, pos);
 }
 
 __device__ __forceinline__ float max8(const uint32_t *v) {
@@ -308,18 +325,18 @@ __global__ void __launch_bounds__(EV_THREADS, 1)
 tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
     extern __shared__ __align__(1024) unsigned char ev_smem[];
     unsigned char *ring = ev_smem;
-    unsigned char *stg_all = ev_smem + EV_STAGES * EV_STAGE_BYTES;     // [16 warps][32 lanes][EV_STG] staged entries
+    unsigned char *stg_all = ev_smem + EV_STAGES * EV_STAGE_BYTES;     // [24 warps][32 lanes][EV_STG] staged entries
     uint64_t *bars = reinterpret_cast<uint64_t *>(stg_all + EV_EPI_WARPS * 32 * EV_STG_BYTES);
     uint64_t *full_bar = bars;                              // [EV_STAGES] item slab landed
     uint64_t *empty_bar = bars + EV_STAGES;                 // [EV_STAGES] both issuers' MMAs on the slab retired
-    // Accumulator slot s is used alternately by the two row blocks of one parity (0/2 share the even slots, 1/3
-    // the odd ones).  A warp may run up to three tiles ahead of a slower warp of its row block, i.e. be waiting
-    // for its row block's NEXT use of a slot while the other row block's use in between has not happened yet; a
-    // single parity bit per slot cannot tell those apart (the wait would pass on the stale phase).  Hence one
-    // full/empty barrier pair per (slot, row-block half): phases then advance once per use BY THAT ROW BLOCK.
-    uint64_t *tfull_bar = bars + 2 * EV_STAGES;             // [EV_SLOTS][2]  accumulator slot complete (for row block rb: index 2*s + (rb >> 1))
-    uint64_t *tempty_bar = tfull_bar + 2 * EV_SLOTS;        // [EV_SLOTS][2]  the four warps of that row block have read it
-    uint64_t *afull_bar = tempty_bar + 2 * EV_SLOTS;        // [EV_RB]        A rows of the unit are in tensor memory
+    // Every row block owns two accumulator slots (2*rb, 2*rb+1) and alternates between them: tile g of the CTA
+    // uses slot 2*rb + (g & 1), barrier phase g >> 1.  (A first version shared six slots between four row blocks;
+    // a warp could then be waiting for its row block's NEXT use of a slot while the other row block's use in
+    // between had not happened yet -- one parity bit cannot tell those apart -- and, worse, a slot was held until
+    // the slowest warp of ANOTHER row block had read it, which serialised MMA and filter.)
+    uint64_t *tfull_bar = bars + 2 * EV_STAGES;             // [EV_SLOTS]  accumulator slot complete
+    uint64_t *tempty_bar = tfull_bar + EV_SLOTS;            // [EV_SLOTS]  the four warps of the row block have read it
+    uint64_t *afull_bar = tempty_bar + EV_SLOTS;            // [EV_RB]     A rows of the unit are in tensor memory
     uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + EV_NUM_BARS);
     volatile uint32_t *s_abort = tmem_base_smem + 1;
     volatile uint32_t *s_trace = s_abort + 1;          // [20] (debug builds)
@@ -332,13 +349,13 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
         *s_abort = 0u;
         for (int s = 0; s < EV_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 2);
+            mbar_init(&empty_bar[s], EV_RB);
         }
-        for (int s = 0; s < 2 * EV_SLOTS; ++s) {
+        for (int s = 0; s < EV_SLOTS; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 4);
+            mbar_init(&tempty_bar[s], 4 * EV_CH);
         }
-        for (int s = 0; s < EV_RB; ++s) mbar_init(&afull_bar[s], 4);
+        for (int s = 0; s < EV_RB; ++s) mbar_init(&afull_bar[s], 4 * EV_CH);
         mbar_fence_init();
     }
     if (warp == EV_MMA_WARP0) tmem_alloc(tmem_base_smem, 512);
@@ -347,12 +364,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
     const int n_units = a.n_row_tiles * a.n_slices;
-    // 640 threads get 96 registers each at launch; the role warpgroup hands 64 of them per thread to the epilogue
-    // warpgroups, whose 64 scores + 8 group maxima + row state do not fit in 96 without spilling in the tile loop
-    // (each role branch starts with its own setmaxnreg: ptxas budgets registers per control-flow region)
-    if (warp >= EV_EPI_WARPS) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(EV_REGS_ROLE));
-      if (warp == EV_TMA_WARP) {
+    if (warp == EV_TMA_WARP) {
         // ================= TMA producer: one 64-item x 64-element fp16 slab per tile =================
         int stage = 0;
         uint32_t phase = 0;
@@ -374,50 +386,39 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                 if (++stage == EV_STAGES) { stage = 0; phase ^= 1u; }
             }
         }
-      } else if (warp == EV_MMA_WARP0 || warp == EV_MMA_WARP0 + 1) {
-        // ================= MMA issuers: warp `me` owns row blocks 2*me and 2*me+1 =================
-        const int me = warp - EV_MMA_WARP0;
+    } else if (warp >= EV_MMA_WARP0) {
+        // ================= MMA issuers: one warp per row block =================
+        const int rb = warp - EV_MMA_WARP0;
         int stage = 0;
         uint32_t phase = 0, uphase = 0;
-        // Use (g, rb) -- g = tiles issued by this CTA so far -- takes slot (4g + rb) % 6; row block rb comes back to
-        // the same slot every third tile, so its barrier phase for tile g is g / 3.  The slot's previous user is
-        // row block rb ^ 2 at tile g - 2 (rb < 2) or g - 1 (rb >= 2).
-        int g = 0;
-        const int rb0 = 2 * me, rb1 = 2 * me + 1;
-        const int half = me;                                 // rb >> 1 of both row blocks of this warp
-        const int back = me == 0 ? 2 : 1;
+        int g = 0;                                           // tiles issued by this CTA so far
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int sl = unit % a.n_slices;
             const int t_lo = sl * a.tiles_per_slice;
             const int t_hi = min(t_lo + a.tiles_per_slice, a.n_col_tiles);
             const int n_t = SEED ? a.n_seed_tiles : (t_hi - t_lo);
-            ev_wait(&afull_bar[rb0], uphase, s_abort, a.dbg, 0x200u | rb0, static_cast<uint32_t>(unit));
-            ev_wait(&afull_bar[rb1], uphase, s_abort, a.dbg, 0x200u | rb1, static_cast<uint32_t>(unit));
+            ev_wait(&afull_bar[rb], uphase, s_abort, a.dbg, 0x200u | rb, static_cast<uint32_t>(unit));
             uphase ^= 1u;
             for (int i = 0; i < n_t; ++i, ++g) {
-                const int slot0 = (4 * g + rb0) % EV_SLOTS, slot1 = (4 * g + rb1) % EV_SLOTS;
+                const int slot = 2 * rb + (g & 1);
                 EV_TRACE(0x51, i);
-                if (g >= back) {
-                    const uint32_t par_prev = static_cast<uint32_t>(((g - back) / 3) & 1);
-                    ev_wait(&tempty_bar[2 * slot0 + (half ^ 1)], par_prev, s_abort, a.dbg, 0x300u | (me << 4) | slot0, static_cast<uint32_t>(i));
-                    ev_wait(&tempty_bar[2 * slot1 + (half ^ 1)], par_prev, s_abort, a.dbg, 0x300u | (me << 4) | slot1, static_cast<uint32_t>(i));
-                }
+                // both probes are in flight before either result is needed (a completed try_wait still costs ~100 clk)
+                const uint32_t par_e = static_cast<uint32_t>(((g >> 1) & 1) ^ 1);
+                const bool ok_e = mbar_try_wait(&tempty_bar[slot], par_e);
+                const bool ok_f = mbar_try_wait(&full_bar[stage], phase);
+                if (!ok_e) ev_wait(&tempty_bar[slot], par_e, s_abort, a.dbg, 0x300u | slot, static_cast<uint32_t>(i));
                 EV_TRACE(0x52, i);
-                ev_wait(&full_bar[stage], phase, s_abort, a.dbg, 0x400u | (me << 4) | stage, static_cast<uint32_t>(i));
+                if (!ok_f) ev_wait(&full_bar[stage], phase, s_abort, a.dbg, 0x400u | (rb << 4) | stage, static_cast<uint32_t>(i));
                 EV_TRACE(0x53, i);
                 tc_fence_after();
                 __syncwarp();
                 if (elect_one()) {
                     const uint64_t db = smem_desc_sw128(ring + stage * EV_STAGE_BYTES);
-                    const uint32_t d0 = tmem_base + EV_ACC0 + slot0 * EV_BN;
-                    const uint32_t d1 = tmem_base + EV_ACC0 + slot1 * EV_BN;
-                    const uint32_t a0 = tmem_base + rb0 * 32, a1 = a0 + 32;
+                    const uint32_t d0 = tmem_base + EV_ACC0 + slot * EV_BN;
+                    const uint32_t a0 = tmem_base + rb * 32;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_ts(d0, a0 + 8 * k, db + 2 * k, EV_IDESC, k > 0 ? 1u : 0u);
-                    umma_commit(&tfull_bar[2 * slot0 + half]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ts(d1, a1 + 8 * k, db + 2 * k, EV_IDESC, k > 0 ? 1u : 0u);
-                    umma_commit(&tfull_bar[2 * slot1 + half]);
+                    umma_commit(&tfull_bar[slot]);
                     umma_commit(&empty_bar[stage]);
                 }
                 __syncwarp();
@@ -425,22 +426,20 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                 if (++stage == EV_STAGES) { stage = 0; phase ^= 1u; }
             }
         }
-      }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EV_REGS_EPI));
-        // ================= epilogue: one thread per user row =================
-        const int rb = warp >> 2;                // 128-row block of the unit
+        // ================= epilogue: two threads per user row, 32 columns of every tile each =================
+        // (One thread per row and tile leaves 3 warps per scheduler, each a long dependent chain -- barrier wait,
+        // TMEM load, max tree, vote -- of ~750 clk per tile: the profile showed the issue ports half idle with the
+        // tensor pipe waiting.  Halving the columns per thread doubles the warps that hide each other's latency.)
+        const int rb = warp >> 3;                // 128-row block of the unit
+        const int h = (warp >> 2) & 1;           // column half of every tile
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
         const int row_local = rb * 128 + q * 32 + lane;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         // the warp's staging area doubles as the histogram of the (rare) overflow compaction
         uint32_t *hist = reinterpret_cast<uint32_t *>(stg_all + warp * 32 * EV_STG_BYTES);
         const uint32_t sbase = smem_u32(stg_all + (warp * 32 + lane) * EV_STG_BYTES);
-        // this row block's slot sequence has period 3 in the tile count: (rb + 4k) % 6, k = g % 3; phase = g / 3
-        const int half = rb >> 1;
-        int slot = rb;
-        int k3 = 0;
-        uint32_t spar = 0;
+        int g = 0;                                            // tiles consumed so far: slot 2*rb + (g & 1), phase g >> 1
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int rt = unit / a.n_slices, sl = unit % a.n_slices;
             const int t_lo = sl * a.tiles_per_slice;
@@ -448,30 +447,30 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
             const int n_t = SEED ? a.n_seed_tiles : (t_hi - t_lo);
             const int64_t row = static_cast<int64_t>(rt) * EV_BM + row_local;
             const bool row_ok = row < a.Ma;
-            // ---- this thread's user row -> tensor memory (columns 32*rb .. 32*rb+31 of its lane).  Every MMA of
-            // the previous unit that read these columns has retired: this warp has seen the accumulator of the
-            // unit's last tile of its row block, and a commit covers all MMAs issued before it.
+            // ---- this thread's half of its user row -> tensor memory (16 of the columns 32*rb .. 32*rb+31 of its
+            // lane).  Every MMA of the previous unit that read these columns has retired: this warp has seen the
+            // accumulator of the unit's last tile of its row block, and a commit covers all MMAs issued before it.
             {
-                uint32_t av[32];
+                uint32_t av[16];
                 if (row_ok) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(a.a16 + row * EV_KPAD);
+                    const uint4 *src = reinterpret_cast<const uint4 *>(a.a16 + row * EV_KPAD + h * 32);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         const uint4 x = src[j];
                         av[4 * j] = x.x; av[4 * j + 1] = x.y; av[4 * j + 2] = x.z; av[4 * j + 3] = x.w;
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) av[j] = 0u;
+                    for (int j = 0; j < 16; ++j) av[j] = 0u;
                 }
-                tmem_st32(lane_base + rb * 32, av);
+                tmem_st16(lane_base + rb * 32 + h * 16, av);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&afull_bar[rb]);
             }
-            // ---- per-row state
-            float tk[EV_SEEDK];                               // seed mode: largest tile maxima, descending
+            // ---- per-list state
+            float tk[EV_SEEDK];                               // seed mode: largest half-tile maxima, descending
             float tau = INFINITY;
             bool give_up = false;
             int r_keep = 0, g_cnt = 0;                        // g_cnt: entries already in the global list
@@ -492,47 +491,33 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                 // Any starting threshold is safe: "every unlisted column scored <= the threshold in force when
                 // it was seen" holds either way, and a row left with too few candidates fails certification.
                 if (!give_up) tau = a.tau0 ? a.tau0[row] : -INFINITY;
-                row_buf = a.lists + (static_cast<size_t>(row_ok ? row : 0) * a.n_slices + sl) * EV_CAP;
+                row_buf = a.lists + ((static_cast<size_t>(row_ok ? row : 0) * a.n_slices + sl) * EV_CH + h) * EV_CAP;
             }
-            for (int i = 0; i < n_t; ++i) {
+            for (int i = 0; i < n_t; ++i, ++g) {
                 const int t = SEED ? (a.seed_off + i * a.seed_stride) : (t_lo + i);
+                const int slot = 2 * rb + (g & 1);
+                const uint32_t spar = static_cast<uint32_t>((g >> 1) & 1);
                 EV_TRACE(1, i);
-                ev_wait(&tfull_bar[2 * slot + half], spar, s_abort, a.dbg, 0x500u | (warp << 4) | slot, static_cast<uint32_t>(i));
+                ev_wait(&tfull_bar[slot], spar, s_abort, a.dbg, 0x500u | (warp << 4) | slot, static_cast<uint32_t>(i));
                 tc_fence_after();
-                const uint32_t taddr = lane_base + EV_ACC0 + slot * EV_BN;
-                uint32_t va[32], vb[32];
+                const uint32_t taddr = lane_base + EV_ACC0 + slot * EV_BN + h * 32;
+                uint32_t v[32];
                 __syncwarp();
                 EV_TRACE(2, i);
-                tmem_ld32(taddr, va);
-                tmem_ld32(taddr + 32, vb);
+                tmem_ld32(taddr, v);
                 tmem_ld_wait();
-                // the 64 scores are in registers: hand the slot back BEFORE filtering
+                // the scores are in registers: hand the slot back BEFORE filtering
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[2 * slot + half]);
-                slot += 4;
-                if (slot >= EV_SLOTS) slot -= EV_SLOTS;
-                if (++k3 == 3) { k3 = 0; spar ^= 1u; }
-                const uint32_t tcol = static_cast<uint32_t>(t) * EV_BN;
-                if (t == a.n_col_tiles - 1 && (a.Nb & (EV_BN - 1)) != 0) {
-                    // zero padding beyond Nb exists in the last column tile only
-                    const uint32_t nb32 = static_cast<uint32_t>(a.Nb);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (tcol + j >= nb32) va[j] = 0xFF800000u;        // -inf
-                        if (tcol + 32 + j >= nb32) vb[j] = 0xFF800000u;
-                    }
-                }
+                if (lane == 0) mbar_arrive(&tempty_bar[slot]);
+                // (zero padding beyond Nb exists in the last column tile only; those columns score exactly 0 and, if
+                // a row lists them, the re-score kernel drops them like any other invalid column)
+                const uint32_t tcol = static_cast<uint32_t>(t) * EV_BN + h * 32;
                 EV_TRACE(3, i);
-                float m8[8];
+                float m8[4];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    m8[g] = max8(va + 8 * g);
-                    m8[4 + g] = max8(vb + 8 * g);
-                }
-                const float mh0 = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
-                const float mh1 = fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]));
-                const float top = fmaxf(mh0, mh1);
+                for (int gq = 0; gq < 4; ++gq) m8[gq] = max8(v + 8 * gq);
+                const float top = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
                 if (SEED) {
                     float x = top;
 #pragma unroll
@@ -542,28 +527,22 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                         tk[s] = hi;
                     }
                 } else if (__any_sync(0xffffffffu, top > tau)) {
-                    // some row of the warp has a candidate in this tile: narrow down to 32-column halves, then to
-                    // 8-column groups, and only there look at single columns
+                    // some row of the warp has a candidate in this half tile: narrow down to 8-column groups, and
+                    // only there look at single columns
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (!__any_sync(0xffffffffu, (h ? mh1 : mh0) > tau)) continue;
-#pragma unroll
-                        for (int gg = 0; gg < 4; ++gg) {
-                            const int g = 4 * h + gg;
-                            if (!__any_sync(0xffffffffu, m8[g] > tau)) continue;
-                            EV_TRACE(4 + g, i);
-                            if (__any_sync(0xffffffffu, saddr - sbase > static_cast<uint32_t>(EV_STG_LIMIT))) {
-                                EV_TRACE(0x20 + g, i);
-                                g_cnt = flush_staged(sbase, saddr, row_buf, g_cnt);
-                                saddr = sbase;
-                            }
-                            const uint32_t *v = h ? (vb + 8 * gg) : (va + 8 * gg);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) append_if_above(saddr, __uint_as_float(v[j]), tau, tcol + 8 * g + j);
+                    for (int gq = 0; gq < 4; ++gq) {
+                        if (!__any_sync(0xffffffffu, m8[gq] > tau)) continue;
+                        EV_TRACE(4 + gq, i);
+                        if (__any_sync(0xffffffffu, saddr - sbase > static_cast<uint32_t>(EV_STG_LIMIT))) {
+                            EV_TRACE(0x20 + gq, i);
+                            g_cnt = flush_staged(sbase, saddr, row_buf, g_cnt);
+                            saddr = sbase;
                         }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) append_if_above(saddr, __uint_as_float(v[8 * gq + j]), tau, tcol + 8 * gq + j);
                     }
                     // A list that gets within a tile of its capacity is cut to its r_keep best.  (Checked once per
-                    // tile: a tile adds at most 64 entries, so a list below the trigger cannot overflow inside it.)
+                    // tile: a tile adds at most 32 entries, so a list below the trigger cannot overflow inside it.)
                     EV_TRACE(0x30, i);
                     if (__any_sync(0xffffffffu, g_cnt + static_cast<int>((saddr - sbase) >> 3) > EV_TRIGGER)) {
                         EV_TRACE(0x31, i);
@@ -582,16 +561,36 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
             }
             // ---- end of unit
             if (SEED) {
-                float v = tk[0];
+                // Both threads of a row publish their sorted half-tile maxima; the k-th largest of the union is a
+                // lower bound of the row's k-th largest sample score.  k depends on how many of the row's top
+                // columns may turn out to be train items.
+                float *mine = a.seed_scratch + ((static_cast<size_t>(blockIdx.x) * EV_BM + row_local) * EV_CH + h) * EV_SEEDK;
 #pragma unroll
-                for (int s = 1; s < EV_SEEDK; ++s)
-                    if (s < a.seed_k) v = tk[s];
-                if (row_ok) a.tau0[row] = v;
+                for (int s = 0; s < EV_SEEDK; ++s) mine[s] = tk[s];
+                __threadfence_block();
+                asm volatile("bar.sync 1, %0;" ::"n"(EV_EPI_WARPS * 32) : "memory");     // epilogue warps only
+                if (h == 0 && row_ok) {
+                    int nmask = 0;
+                    if (a.mask_rowptr != nullptr) {
+                        const int64_t len = a.mask_rowptr[row + 1] - a.mask_rowptr[row];
+                        nmask = len < EV_SEED_TAB - 1 ? static_cast<int>(len) : EV_SEED_TAB - 1;
+                    }
+                    const int kk = a.seed_k[nmask];
+                    const float *other = mine + EV_SEEDK;
+                    int ia = 0, ib = 0;
+                    float vsel = -INFINITY;
+                    for (int s = 0; s < kk; ++s) {            // two-pointer merge of two descending lists
+                        const float xa = ia < EV_SEEDK ? mine[ia] : -INFINITY;
+                        const float xb = ib < EV_SEEDK ? other[ib] : -INFINITY;
+                        if (xa >= xb) { vsel = xa; ++ia; } else { vsel = xb; ++ib; }
+                    }
+                    a.tau0[row] = vsel;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(EV_EPI_WARPS * 32) : "memory");     // scratch may be overwritten now
             } else {
                 g_cnt = flush_staged(sbase, saddr, row_buf, g_cnt);
-                if (__any_sync(0xffffffffu, g_cnt > EV_CAP)) {}      // (cannot happen: flushes keep lists below the trigger + staging)
                 if (row_ok) {
-                    const size_t o = static_cast<size_t>(row) * a.n_slices + sl;
+                    const size_t o = (static_cast<size_t>(row) * a.n_slices + sl) * EV_CH + h;
                     a.cnt_out[o] = give_up ? 0 : g_cnt;
                     a.tau_out[o] = give_up ? INFINITY : tau;
                 }
@@ -677,7 +676,7 @@ struct RescoreArgs {
     const float *B;
     int64_t Ma, Nb;
     int D, K, n_slices, kp;
-    const uint64_t *lists;     // [Ma][n_slices][EV_CAP]
+    const uint64_t *lists;     // [Ma][n_slices][EV_CAP]   (n_slices = column slices x threads per row)
     const int32_t *cnt;        // [Ma][n_slices]
     const float *tau;          // [Ma][n_slices]
     const float *a_norm;       // [Ma] scaled row norms (upper bounds)
@@ -746,7 +745,7 @@ __global__ void __launch_bounds__(kRescoreWarps * 32) rescore_lists_kernel(const
             bool v = key != 0ull && static_cast<uint32_t>(key >> 32) >= prefix;
             if (v) {
                 const int64_t col = key_index(key);
-                if (col == self_col) v = false;
+                if (col == self_col || col >= a.Nb) v = false;
                 int lo = 0, hi = nm_all;                      // binary search in the row's sorted train items
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
@@ -915,8 +914,9 @@ size_t tc_eval_workspace_bytes(int64_t Ma, int64_t Nb, int D) {
     n += al256(static_cast<size_t>(Nb) * EV_KPAD * 2);                  // B fp16
     n += 2 * al256(static_cast<size_t>(Ma) * 4) + 256;                  // A norms and scales, B stats
     n += al256(static_cast<size_t>(Ma) * 4);                            // starting thresholds
-    n += 2048 + al256(static_cast<size_t>(Ma) * slices * EV_CAP * 8);   // candidate lists (2 KB aligned)
-    n += 2 * al256(static_cast<size_t>(Ma) * slices * 4);               // list lengths, final thresholds
+    n += 2048 + al256(static_cast<size_t>(Ma) * slices * EV_CH * EV_CAP * 8);   // candidate lists (2 KB aligned)
+    n += 2 * al256(static_cast<size_t>(Ma) * slices * EV_CH * 4);       // list lengths, final thresholds
+    n += al256(static_cast<size_t>(sm_count()) * EV_BM * EV_CH * EV_SEEDK * 4);   // seed pass: half-tile maxima of a unit
     n += al256(static_cast<size_t>(Ma) * 4);                            // fallback row list
     n += al256(static_cast<size_t>(Ma) * 8);                            // ... and their seed keys
     n += rank_listed_workspace_bytes(D);                                // exact engine for uncertified rows
@@ -942,9 +942,10 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     float *b_stats = reinterpret_cast<float *>(ws); ws += 256;
     float *tau0 = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
     ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ws) + 2047) & ~static_cast<uintptr_t>(2047));
-    uint64_t *lists = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * EV_CAP * 8);
-    int32_t *cnt = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * 4);
-    float *tau = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * 4);
+    uint64_t *lists = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * EV_CH * EV_CAP * 8);
+    int32_t *cnt = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * EV_CH * 4);
+    float *tau = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * EV_CH * 4);
+    float *seed_scratch = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(sm_count()) * EV_BM * EV_CH * EV_SEEDK * 4);
     int32_t *fb_rows = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
     uint64_t *fb_seeds = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 8);
     void *rank_ws = ws;
@@ -988,6 +989,7 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     t.kp = kp;
     t.lists = lists; t.cnt_out = cnt; t.tau_out = tau; t.tau0 = nullptr;
     t.dbg = counters + 36;
+    t.seed_scratch = seed_scratch;
 
     const size_t smem = ev_smem_bytes();
     cudaError_t ce = cudaFuncSetAttribute(tc_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -1002,9 +1004,11 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     // short fail certification and go to the exact engine.  The sample is sized so that k <= 16 tile maxima.
     int seed_tiles = 256;
     if (const char *env = getenv("CHAOREC_TC_SEED_TILES")) seed_tiles = atoi(env);
-    const double need = kp + 24.0;
+    // columns a row needs above its threshold: K, the columns inside the certification window and the slack the
+    // approximate order needs (6), plus every train item of the row (a trained model ranks them at the top)
+    const double need0 = e.K + 6.0 + (e.exclude_self ? 1.0 : 0.0);
     {
-        const int cap = static_cast<int>(6.0 / need * t.n_col_tiles);       // need * f <= 6  ->  k <= 16
+        const int cap = static_cast<int>(8.5 / (need0 + 16.0) * t.n_col_tiles);   // (need0 + 16) * f <= 8.5 -> k <= 20
         if (seed_tiles > cap) seed_tiles = cap;
         if (seed_tiles > t.n_col_tiles / 2) seed_tiles = t.n_col_tiles / 2;
     }
@@ -1016,10 +1020,13 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
         p.seed_stride = t.n_col_tiles / seed_tiles;
         p.seed_off = p.seed_stride / 2;
         const double f = static_cast<double>(seed_tiles) * EV_BN / static_cast<double>(e.Nb);
-        int k_seed = poisson_rank(need * f, 1e-3);
-        if (k_seed < 2) k_seed = 2;
-        if (k_seed > EV_SEEDK) k_seed = EV_SEEDK;
-        p.seed_k = k_seed;
+        const int k_max = seed_tiles < EV_SEEDK ? seed_tiles : EV_SEEDK;
+        for (int m = 0; m < EV_SEED_TAB; ++m) {
+            int k_seed = poisson_rank((need0 + m) * f, 1e-3);
+            if (k_seed < 2) k_seed = 2;
+            if (k_seed > k_max) k_seed = k_max;      // (rows that would need more are left short and fall back)
+            p.seed_k[m] = static_cast<unsigned char>(k_seed);
+        }
         p.tau0 = tau0;
         const int pgrid = p.n_row_tiles < sm_count() ? p.n_row_tiles : sm_count();
         tc_eval_kernel<true><<<pgrid, EV_THREADS, smem, stm>>>(map_b, p);
@@ -1032,7 +1039,7 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     }
 
     RescoreArgs r{};
-    r.A = e.A; r.B = e.B; r.Ma = e.Ma; r.Nb = e.Nb; r.D = e.d; r.K = e.K; r.n_slices = slices; r.kp = kp;
+    r.A = e.A; r.B = e.B; r.Ma = e.Ma; r.Nb = e.Nb; r.D = e.d; r.K = e.K; r.n_slices = slices * EV_CH; r.kp = kp;
     r.lists = lists; r.cnt = cnt; r.tau = tau; r.a_norm = a_norm; r.a_scale = a_scale; r.b_stats = b_stats;
     // |s~' - s'| <= gamma |a'||b'|max in scaled units, against the CANONICAL fp32 score s':
     //   fp16 rounding of both operands      2 * 2^-11 + 2^-22
@@ -1047,7 +1054,7 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     r.abort_flag = counters + 36;
     {
         int keys_per_warp = 512;                                   // a power of two >= all listed entries of a row
-        while (keys_per_warp < slices * EV_CAP) keys_per_warp <<= 1;
+        while (keys_per_warp < slices * EV_CH * EV_CAP) keys_per_warp <<= 1;
         const size_t rs_smem = static_cast<size_t>(kRescoreWarps) * (keys_per_warp * 8 + 256 * 4);
         ce = cudaFuncSetAttribute(rescore_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rs_smem));
         if (ce != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }

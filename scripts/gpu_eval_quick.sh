@@ -25,7 +25,7 @@ for (U, I, d, K) in ((1500, 70000, 64, 20), (700, 2500, 64, 20), (3000, 5000, 64
 PY
 timeout 150 python /tmp/tiny.py > gpurun_out/tiny.log 2>&1; echo "tiny rc=$?" >> gpurun_out/tiny.log; tail -8 gpurun_out/tiny.log
 if [ "$1" = "tiny" ]; then exit 0; fi
-if [ "$1" != "notests" ]; then
+if [ "$1" != "notests" ] && [ "$1" != "ncu" ]; then
   timeout 900 python -m pytest tests/test_gpu_ranking.py -x -q -m gpu -p no:cacheprovider --timeout 300 -k "not exact" > gpurun_out/pytest_rank.log 2>&1; tail -6 gpurun_out/pytest_rank.log
 fi
 cat > /tmp/evaltime.py <<'PY'
@@ -41,7 +41,8 @@ it = torch.randn(I, d, device=dev, generator=g) * 0.1
 mu = torch.arange(U, device=dev).repeat_interleave(16)
 mi = torch.randint(0, I, (U * 16,), device=dev, generator=g)
 mask = cb.mask_csr_from_edges(mu, mi, U, I)
-for rep in range(4):
+import os
+for rep in range(2 if os.environ.get('NCU') else 4):
     st = {}
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -53,11 +54,11 @@ cb.rank_topk(u, it, mask, K, 1e-6, U, stats=st); print(st)
 PY
 timeout 200 python /tmp/evaltime.py > gpurun_out/evaltime.log 2>&1; tail -6 gpurun_out/evaltime.log
 if [ "$1" != "ncu" ]; then exit 0; fi
-(timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/eval_launches.csv python /tmp/evaltime.py) > gpurun_out/eval_ncu.log 2>&1
+(NCU=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/eval_launches.csv python /tmp/evaltime.py) > gpurun_out/eval_ncu.log 2>&1
 python - <<'PY'
 import csv, collections
 rows = [r for r in csv.reader(open('gpurun_out/eval_launches.csv')) if len(r) > 5 and r[0].isdigit()]
 agg = collections.OrderedDict()
-for r in rows[-12:]:
+for r in rows[-14:]:
     print(r[4][:70], r[-1])
 PY
