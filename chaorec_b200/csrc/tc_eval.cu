@@ -262,27 +262,6 @@ __device__ __forceinline__ uint32_t select_prefix(LoadKey key_at, int n, int r, 
     return prefix;
 }
 
-// Overflow protection inside the MMA kernel (rare: a list only gets near its capacity when the starting
-// threshold was far too low): keep the entries of one row's list whose score reaches the (r+1)-th largest.
-__device__ __forceinline__ void compact_list(uint64_t *row_buf, int n, int r, int lane, uint32_t *hist, int &new_cnt,
-                                             float &new_tau) {
-    const uint32_t prefix = select_prefix([&](int i) { return key_of_raw(row_buf[i]); }, n, r, lane, hist);
-    // stable in-place compaction, 32 entries per step (reads of a step complete before its writes)
-    int kept = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const uint64_t raw = (i < n) ? row_buf[i] : 0ull;
-        const bool keep = i < n && static_cast<uint32_t>(key_of_raw(raw) >> 32) >= prefix;
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        __syncwarp();
-        if (keep) row_buf[kept + __popc(m & ((1u << lane) - 1u))] = raw;
-        kept += __popc(m);
-        __syncwarp();
-    }
-    new_cnt = kept;
-    new_tau = score_of_bits(prefix);
-}
-
 // Rare paths of the epilogue, kept out of line so that the tile loop stays small.
 // (1) Move every lane's staged entries to the end of its global list; returns the new list length.
 __device__ __forceinline__ int flush_staged(uint32_t sbase, uint32_t saddr, uint64_t *row_buf, int g_cnt) {
@@ -295,31 +274,6 @@ __device__ __forceinline__ int flush_staged(uint32_t sbase, uint32_t saddr, uint
     }
     return g_cnt + n;
 }
-// (2) A list within a tile of its capacity (the starting threshold was far too low) is cut to its r_keep best at
-// once.  Returns the new length in the low half and the new threshold's bits in the high half; length 0xFFFF =
-// give up (a huge run of exact ties).  `hist` may alias the warp's (just flushed) staging buffers.
-__device__ __forceinline__ uint64_t overflow_compact(uint64_t *row_buf, int g_cnt, int r_keep, float tau, int lane, uint32_t *hist) {
-    unsigned need = __ballot_sync(0xffffffffu, g_cnt > EV_TRIGGER);
-    uint32_t out_cnt = static_cast<uint32_t>(g_cnt);
-    float out_tau = tau;
-    while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const int n_src = __shfl_sync(0xffffffffu, g_cnt, src);
-        const int r_src = __shfl_sync(0xffffffffu, r_keep, src);
-        const uint64_t buf_bits = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(row_buf), src);
-        int nc;
-        float nt;
-        __syncwarp();                                    // the flushed entries are visible to the whole warp
-        compact_list(reinterpret_cast<uint64_t *>(buf_bits), n_src, r_src, lane, hist, nc, nt);
-        if (lane == src) {
-            out_cnt = nc > EV_TRIGGER ? 0xFFFFu : static_cast<uint32_t>(nc);
-            out_tau = nt;
-        }
-    }
-    return (static_cast<uint64_t>(__float_as_uint(out_tau)) << 32) | out_cnt;
-}
-
 template <bool SEED>
 __global__ void __launch_bounds__(EV_THREADS, 1)
 tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
@@ -436,8 +390,6 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
         const int row_local = rb * 128 + q * 32 + lane;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        // the warp's staging area doubles as the histogram of the (rare) overflow compaction
-        uint32_t *hist = reinterpret_cast<uint32_t *>(stg_all + warp * 32 * EV_STG_BYTES);
         const uint32_t sbase = smem_u32(stg_all + (warp * 32 + lane) * EV_STG_BYTES);
         int g = 0;                                            // tiles consumed so far: slot 2*rb + (g & 1), phase g >> 1
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -470,7 +422,8 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                 if (lane == 0) mbar_arrive(&afull_bar[rb]);
             }
             // ---- per-list state
-            float tk[EV_SEEDK];                               // seed mode: largest half-tile maxima, descending
+            float tk[EV_SEEDK];                               // seed mode: largest half-tile-pair maxima, descending
+            float pend = -INFINITY;                           // seed mode: maximum of the pair's first half tile
             float tau = INFINITY;
             bool give_up = false;
             int r_keep = 0, g_cnt = 0;                        // g_cnt: entries already in the global list
@@ -519,12 +472,19 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                 for (int gq = 0; gq < 4; ++gq) m8[gq] = max8(v + 8 * gq);
                 const float top = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
                 if (SEED) {
-                    float x = top;
+                    // one insertion per PAIR of half tiles (the k-th largest pair maximum is still a lower bound of
+                    // the k-th largest sample score): halves the cost of the insertion network
+                    if ((i & 1) == 0 && i + 1 < n_t) {
+                        pend = top;
+                    } else {
+                        float x = fmaxf(top, pend);
+                        pend = -INFINITY;
 #pragma unroll
-                    for (int s = 0; s < EV_SEEDK; ++s) {
-                        const float hi = fmaxf(tk[s], x);
-                        x = fminf(tk[s], x);
-                        tk[s] = hi;
+                        for (int s = 0; s < EV_SEEDK; ++s) {
+                            const float hi = fmaxf(tk[s], x);
+                            x = fminf(tk[s], x);
+                            tk[s] = hi;
+                        }
                     }
                 } else if (__any_sync(0xffffffffu, top > tau)) {
                     // some row of the warp has a candidate in this half tile: narrow down to 8-column groups, and
@@ -537,24 +497,13 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                             EV_TRACE(0x20 + gq, i);
                             g_cnt = flush_staged(sbase, saddr, row_buf, g_cnt);
                             saddr = sbase;
+                            // A list that gets within a tile of its capacity means the starting threshold was far
+                            // too low for this row: the row is handed to the exact engine.  (No compaction inside the
+                            // MMA kernel: it is ~600 instructions that would sit in the middle of the hot loop.)
+                            if (g_cnt > EV_TRIGGER) { give_up = true; tau = INFINITY; }
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) append_if_above(saddr, __uint_as_float(v[8 * gq + j]), tau, tcol + 8 * gq + j);
-                    }
-                    // A list that gets within a tile of its capacity is cut to its r_keep best.  (Checked once per
-                    // tile: a tile adds at most 32 entries, so a list below the trigger cannot overflow inside it.)
-                    EV_TRACE(0x30, i);
-                    if (__any_sync(0xffffffffu, g_cnt + static_cast<int>((saddr - sbase) >> 3) > EV_TRIGGER)) {
-                        EV_TRACE(0x31, i);
-                        g_cnt = flush_staged(sbase, saddr, row_buf, g_cnt);
-                        saddr = sbase;
-                        __syncwarp();
-                        const uint64_t r = overflow_compact(row_buf, g_cnt, r_keep, tau, lane, hist);
-                        g_cnt = static_cast<int>(r & 0xFFFFu);
-                        tau = __uint_as_float(static_cast<uint32_t>(r >> 32));
-                        if (g_cnt == 0xFFFF) { give_up = true; tau = INFINITY; g_cnt = 0; }
-                        __syncwarp();                             // the histogram space is staging space again
-                        EV_TRACE(0x32, i);
                     }
                 }
                 EV_TRACE(0x40, i);

@@ -22,6 +22,15 @@ for (U, I, d, K) in ((1500, 70000, 64, 20), (700, 2500, 64, 20), (3000, 5000, 64
     cidx, csc = canon.score_mask_topk(u.numpy(), it.numpy(), mask.rowptr.cpu().numpy(), mask.col.cpu().numpy(), 1e-6, K, 0)
     ok = np.array_equal(idx.cpu().numpy(), cidx) and np.array_equal(sc.cpu().numpy().view(np.uint32), csc.view(np.uint32))
     print((U, I, d, K), st, 'MATCH' if ok else 'MISMATCH', flush=True)
+    if not ok:
+        gi, gs = idx.cpu().numpy(), sc.cpu().numpy()
+        bad = np.nonzero((gi != cidx).any(1))[0]
+        print('  bad rows', len(bad), bad[:10])
+        r = bad[0]
+        print('  row', r, 'gpu', gi[r].tolist(), '\n  canon', cidx[r].tolist())
+        print('  gpu sc', gs[r][:8], 'canon sc', csc[r][:8])
+        miss = [c for c in cidx[r].tolist() if c not in gi[r].tolist()]
+        print('  missing cols', miss, 'tiles', [c // 64 for c in miss], 'mask', sorted(mask.col[mask.rowptr[r]:mask.rowptr[r+1]].cpu().tolist()))
 PY
 timeout 150 python /tmp/tiny.py > gpurun_out/tiny.log 2>&1; echo "tiny rc=$?" >> gpurun_out/tiny.log; tail -8 gpurun_out/tiny.log
 if [ "$1" = "tiny" ]; then exit 0; fi

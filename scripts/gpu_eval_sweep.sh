@@ -12,6 +12,10 @@ g = torch.Generator(device=dev).manual_seed(1)
 u = torch.randn(U, d, device=dev, generator=g) * 0.1
 it = torch.randn(I, d, device=dev, generator=g) * 0.1
 mu = torch.arange(U, device=dev).repeat_interleave(16)
+import os
+U = int(os.environ.get('EVAL_U', U))
+u = u[:U]
+mu = torch.arange(U, device=dev).repeat_interleave(16)
 mi = torch.randint(0, I, (U * 16,), device=dev, generator=g)
 mask = cb.mask_csr_from_edges(mu, mi, U, I)
 for rep in range(2):
@@ -20,7 +24,7 @@ for rep in range(2):
 print(st)
 PY
 for st in ${@:-256 512}; do
-  (NCU=1 CHAOREC_TC_SEED_TILES=$st timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/sweep_$st.csv python /tmp/evalsweep.py) > gpurun_out/sweep_$st.log 2>&1
+  (NCU=1 CHAOREC_TC_SEED_TILES=$st CHAOREC_TC_DEBUG=${DEBUG:-0} timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/sweep_$st.csv python /tmp/evalsweep.py) > gpurun_out/sweep_$st.log 2>&1
   python - <<PY
 import csv
 rows = [r for r in csv.reader(open('gpurun_out/sweep_$st.csv')) if len(r) > 5 and r[0].isdigit()]

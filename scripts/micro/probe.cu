@@ -301,6 +301,85 @@ void run_mma(const char *name, int sms) {
     fflush(stdout);
 }
 
+// The evaluation kernel's issue pattern: NI issuing warps, warp w owns row block w (A at TMEM columns 32*w) and DEPTH
+// private accumulator slots; one commit per tile of 4 MMAs (K = 64); the warp waits for the commit DEPTH tiles back
+// before it reuses a slot.  No TMA, no epilogue: the B slab is static shared memory.
+template <int NI, int DEPTH, bool ONE_LANE_WAIT>
+__global__ void __launch_bounds__(128, 1) mma_probe2(int tiles, uint32_t seed) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *sb = smem;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 8192);     // [NI][DEPTH]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    uint32_t s = seed + threadIdx.x * 2654435761u + blockIdx.x * 40503u;
+    for (int i = threadIdx.x; i < 8192 / 4; i += blockDim.x) {
+        s = s * 1664525u + 1013904223u;
+        reinterpret_cast<uint32_t *>(smem)[i] = 0x3C003C00u | (s & 0x83FF83FFu);
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NI * DEPTH; ++i) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) tmem_alloc(tmem_slot, 512);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = *tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t idesc = make_idesc(64, 1, 1);
+    if (warp < NI) {
+        const uint64_t db = smem_desc(sb);
+        int ls = 0;
+        uint32_t par = 0;
+        for (int t = 0; t < tiles; ++t) {
+            uint64_t *bar = &bars[warp * DEPTH + ls];
+            if (t >= DEPTH) {
+                if (ONE_LANE_WAIT) { if (lane == 0) mbar_wait(bar, par ^ 1u); __syncwarp(); }
+                else mbar_wait(bar, par ^ 1u);
+            }
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d = tb + 32 * NI + (warp * DEPTH + ls) * 64;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ts(d, tb + warp * 32 + k * 8, db + 2 * k, idesc, k > 0);
+                umma_commit(bar);
+            }
+            __syncwarp();
+            if (++ls == DEPTH) { ls = 0; par ^= 1u; }
+        }
+        // drain
+        for (int i = 0; i < DEPTH && i < tiles; ++i) {
+            mbar_wait(&bars[warp * DEPTH + ls], par ^ 1u);
+            if (++ls == DEPTH) { ls = 0; par ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tb, 512);
+}
+
+template <int NI, int DEPTH, bool ONE_LANE_WAIT>
+void run_mma2(const char *name, int sms) {
+    const int tiles = 40000;
+    const size_t smem = 8192 + 256;
+    auto kern = mma_probe2<NI, DEPTH, ONE_LANE_WAIT>;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    kern<<<sms, 128, smem>>>(2000, 1u);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    kern<<<sms, 128, smem>>>(tiles, 7u);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double mmas = 4.0 * NI * tiles;
+    printf("mma2 %-40s %8.3f ms  %7.1f ns per tile, %6.1f clk per MMA @1.965 (chip-wide: %d issuers)\n", name, ms, ms * 1e6 / tiles,
+           ms * 1e6 / mmas * 1.965, NI);
+    fflush(stdout);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // (3) TS-form correctness, fp16 accumulators, pack::16b layout
 // ------------------------------------------------------------------------------------------------------
@@ -520,6 +599,11 @@ mma_only:
         RUN(run_mma<true, 128, 1, 1, 0>("TS N=128 f32", sms));
         RUN(run_mma<false, 256, 1, 1, 0>("SS N=256 f32", sms));
         RUN(run_mma<true, 192, 1, 1, 0>("TS N=192 f32", sms));
+        RUN((run_mma2<2, 3, false>("2 issuers, 3 slots, commit per 4 MMAs", sms)));
+        RUN((run_mma2<2, 3, true>("2 issuers, 3 slots, lane-0 wait", sms)));
+        RUN((run_mma2<3, 2, false>("3 issuers, 2 slots", sms)));
+        RUN((run_mma2<1, 3, false>("1 issuer, 3 slots", sms)));
+        RUN((run_mma2<4, 1, false>("4 issuers, 1 slot each (fully serial per issuer)", sms)));
     }
     printf("done\n");
     return 0;

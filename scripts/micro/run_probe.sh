@@ -14,7 +14,7 @@ if [ "${1:-all}" != "ts" ]; then
   (nvidia-smi --query-gpu=clocks.sm,power.draw --format=csv,noheader -lms 500 > gpurun_out/probe_clocks.csv) &
   SMI=$!
   if [ "${1:-all}" = "mma" ]; then
-    for i in 0 1 2 3 4 5 6 7 8 9 10 11 12; do
+    for i in ${MMA_IDS:-0 1 2 3 4 5 6 7 8 9 10 11 12 13 14 15 16 17}; do
       timeout 20 scripts/micro/probe.bin mma $i >> $OUT 2>&1 || echo "mma variant $i FAILED rc=$?" >> $OUT
     done
   else
