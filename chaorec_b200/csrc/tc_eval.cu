@@ -138,6 +138,45 @@ __device__ __forceinline__ void ev_wait(uint64_t *bar, uint32_t parity, volatile
     }
 }
 
+// Epilogue flavour of the bounded wait, on a precomputed shared-memory address: the common case (phase complete) is a
+// single try_wait and a branch.
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void ev_wait_slow_a(uint32_t bar_addr, uint32_t parity, volatile uint32_t *s_abort, unsigned int *dbg, uint32_t code,
+                                            uint32_t pos) {
+    uint32_t n = 0;
+    unsigned long long t0 = 0;
+    while (!mbar_try_wait_a(bar_addr, parity)) {
+        if ((++n & 63u) != 0u) continue;
+        if (*s_abort) return;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t0 == 0) t0 = t1;
+        if (t1 - t0 > EV_WAIT_NS) {
+            *s_abort = 1u;
+            if (dbg != nullptr && atomicExch(&dbg[0], 1u) == 0u) {
+                dbg[1] = code;
+                dbg[2] = pos;
+                dbg[3] = blockIdx.x;
+                dbg[4] = parity;
+                dbg[7] = threadIdx.x;
+            }
+            return;
+        }
+    }
+}
+
 __device__ __forceinline__ float max8(const uint32_t *v) {
     float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
@@ -391,7 +430,11 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
         const int row_local = rb * 128 + q * 32 + lane;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const uint32_t sbase = smem_u32(stg_all + (warp * 32 + lane) * EV_STG_BYTES);
-        int g = 0;                                            // tiles consumed so far: slot 2*rb + (g & 1), phase g >> 1
+        // tile g of the CTA uses slot 2*rb + (g & 1), phase g >> 1; units have even tile counts
+        const uint32_t bar_full0 = smem_u32(&tfull_bar[2 * rb]), bar_empty0 = smem_u32(&tempty_bar[2 * rb]);
+        const uint32_t taddr0 = lane_base + EV_ACC0 + (2 * rb) * EV_BN + h * 32;
+        const bool lane0 = lane == 0;
+        uint32_t spar = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int rt = unit / a.n_slices, sl = unit % a.n_slices;
             const int t_lo = sl * a.tiles_per_slice;
@@ -446,27 +489,21 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                 if (!give_up) tau = a.tau0 ? a.tau0[row] : -INFINITY;
                 row_buf = a.lists + ((static_cast<size_t>(row_ok ? row : 0) * a.n_slices + sl) * EV_CH + h) * EV_CAP;
             }
-            for (int i = 0; i < n_t; ++i, ++g) {
-                const int t = SEED ? (a.seed_off + i * a.seed_stride) : (t_lo + i);
-                const int slot = 2 * rb + (g & 1);
-                const uint32_t spar = static_cast<uint32_t>((g >> 1) & 1);
-                EV_TRACE(1, i);
-                ev_wait(&tfull_bar[slot], spar, s_abort, a.dbg, 0x500u | (warp << 4) | slot, static_cast<uint32_t>(i));
+            // One visit = one half tile.  The loop is unrolled over the row block's two accumulator slots (tile counts
+            // are even), so barrier / TMEM addresses are loop constants and the phase parity flips once per pair.
+            auto visit = [&](const uint32_t bar_full, const uint32_t bar_empty, const uint32_t taddr, const int i, const uint32_t tcol) {
+                if (!mbar_try_wait_a(bar_full, spar)) ev_wait_slow_a(bar_full, spar, s_abort, a.dbg, 0x500u | (warp << 4), static_cast<uint32_t>(i));
                 tc_fence_after();
-                const uint32_t taddr = lane_base + EV_ACC0 + slot * EV_BN + h * 32;
                 uint32_t v[32];
                 __syncwarp();
-                EV_TRACE(2, i);
                 tmem_ld32(taddr, v);
                 tmem_ld_wait();
                 // the scores are in registers: hand the slot back BEFORE filtering
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[slot]);
-                // (zero padding beyond Nb exists in the last column tile only; those columns score exactly 0 and, if
+                if (lane0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_empty) : "memory");
+                // (zero padding beyond Nb exists in the last column tiles only; those columns score exactly 0 and, if
                 // a row lists them, the re-score kernel drops them like any other invalid column)
-                const uint32_t tcol = static_cast<uint32_t>(t) * EV_BN + h * 32;
-                EV_TRACE(3, i);
                 float m8[4];
 #pragma unroll
                 for (int gq = 0; gq < 4; ++gq) m8[gq] = max8(v + 8 * gq);
@@ -474,11 +511,10 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                 if (SEED) {
                     // one insertion per PAIR of half tiles (the k-th largest pair maximum is still a lower bound of
                     // the k-th largest sample score): halves the cost of the insertion network
-                    if ((i & 1) == 0 && i + 1 < n_t) {
+                    if ((i & 1) == 0) {
                         pend = top;
                     } else {
                         float x = fmaxf(top, pend);
-                        pend = -INFINITY;
 #pragma unroll
                         for (int s = 0; s < EV_SEEDK; ++s) {
                             const float hi = fmaxf(tk[s], x);
@@ -492,9 +528,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
 #pragma unroll
                     for (int gq = 0; gq < 4; ++gq) {
                         if (!__any_sync(0xffffffffu, m8[gq] > tau)) continue;
-                        EV_TRACE(4 + gq, i);
                         if (__any_sync(0xffffffffu, saddr - sbase > static_cast<uint32_t>(EV_STG_LIMIT))) {
-                            EV_TRACE(0x20 + gq, i);
                             g_cnt = flush_staged(sbase, saddr, row_buf, g_cnt);
                             saddr = sbase;
                             // A list that gets within a tile of its capacity means the starting threshold was far
@@ -506,7 +540,16 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                         for (int j = 0; j < 8; ++j) append_if_above(saddr, __uint_as_float(v[8 * gq + j]), tau, tcol + 8 * gq + j);
                     }
                 }
-                EV_TRACE(0x40, i);
+            };
+            {
+                uint32_t tcol = (SEED ? static_cast<uint32_t>(a.seed_off) : static_cast<uint32_t>(t_lo)) * EV_BN + h * 32;
+                const uint32_t dcol = (SEED ? static_cast<uint32_t>(a.seed_stride) : 1u) * EV_BN;
+                for (int i = 0; i < n_t; i += 2) {
+                    visit(bar_full0, bar_empty0, taddr0, i, tcol);
+                    visit(bar_full0 + 8, bar_empty0 + 8, taddr0 + EV_BN, i + 1, tcol + dcol);
+                    tcol += 2 * dcol;
+                    spar ^= 1u;
+                }
             }
             // ---- end of unit
             if (SEED) {
@@ -929,9 +972,12 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     EvalArgs t{};
     t.Ma = e.Ma; t.Nb = e.Nb;
     t.n_row_tiles = static_cast<int>((e.Ma + EV_BM - 1) / EV_BM);
-    t.n_col_tiles = static_cast<int>((e.Nb + EV_BN - 1) / EV_BN);
+    // (tile counts are even everywhere: the epilogue's tile loop is unrolled over the row block's two accumulator
+    // slots; a padding tile beyond Nb scores 0 everywhere and the re-score kernel drops its columns)
+    const int real_col_tiles = static_cast<int>((e.Nb + EV_BN - 1) / EV_BN);
+    t.n_col_tiles = (real_col_tiles + 1) & ~1;
     t.n_slices = slices;
-    t.tiles_per_slice = (t.n_col_tiles + slices - 1) / slices;
+    t.tiles_per_slice = (((t.n_col_tiles + slices - 1) / slices) + 1) & ~1;
     t.a16 = a16;
     t.mask_rowptr = e.mask_rowptr;
     t.exclude_self = e.exclude_self;
@@ -957,16 +1003,17 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     // approximate order needs (6), plus every train item of the row (a trained model ranks them at the top)
     const double need0 = e.K + 6.0 + (e.exclude_self ? 1.0 : 0.0);
     {
-        const int cap = static_cast<int>(8.5 / (need0 + 16.0) * t.n_col_tiles);   // (need0 + 16) * f <= 8.5 -> k <= 20
+        const int cap = static_cast<int>(8.5 / (need0 + 16.0) * real_col_tiles);   // (need0 + 16) * f <= 8.5 -> k <= 20
         if (seed_tiles > cap) seed_tiles = cap;
-        if (seed_tiles > t.n_col_tiles / 2) seed_tiles = t.n_col_tiles / 2;
+        if (seed_tiles > real_col_tiles / 2) seed_tiles = real_col_tiles / 2;
+        seed_tiles &= ~1;
     }
     if (seed_tiles >= 2) {
         EvalArgs p = t;
         p.n_slices = 1;
         p.tiles_per_slice = t.n_col_tiles;
         p.n_seed_tiles = seed_tiles;
-        p.seed_stride = t.n_col_tiles / seed_tiles;
+        p.seed_stride = real_col_tiles / seed_tiles;
         p.seed_off = p.seed_stride / 2;
         const double f = static_cast<double>(seed_tiles) * EV_BN / static_cast<double>(e.Nb);
         const int k_max = seed_tiles < EV_SEEDK ? seed_tiles : EV_SEEDK;
