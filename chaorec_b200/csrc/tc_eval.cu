@@ -40,7 +40,7 @@ constexpr int EV_BM = 384;                        // user rows per unit (3 MMA r
 constexpr int EV_BN = 64;                         // item columns per tile
 constexpr int EV_RB = 3;
 constexpr int EV_KPAD = 64;                       // inner dimension of the fp16 copies (d zero-padded)
-constexpr int EV_STAGES = 12;                     // item-slab ring
+constexpr int EV_STAGES = 8;                      // item-slab ring
 constexpr int EV_STAGE_BYTES = EV_BN * EV_KPAD * 2;
 constexpr int EV_SLOTS = 2 * EV_RB;               // accumulator slots (128 lanes x 64 columns): two private ones per row block
 constexpr int EV_ACC0 = 32 * EV_RB;               // TMEM columns [0,96) hold A: row block rb at 32*rb
@@ -53,9 +53,9 @@ constexpr int EV_MMA_WARP0 = EV_EPI_WARPS + 1;    // warps 25, 26, 27 issue the 
 constexpr int EV_THREADS = (EV_EPI_WARPS + 1 + EV_RB) * 32;   // 896 threads -> 72 registers each
 constexpr int EV_SEEDK = 20;                      // tile maxima kept per row in seed mode
 constexpr int EV_SEED_TAB = 128;                  // per-row seed rank is looked up by the row's train-item count
-constexpr int EV_STG = 16;                        // entries of a list's shared-memory staging buffer
+constexpr int EV_STG = 24;                        // entries of a list's shared-memory staging buffer
 constexpr int EV_STG_BYTES = EV_STG * 8;
-constexpr int EV_STG_LIMIT = (EV_STG - 8) * 8;    // flush before a group of 8 appends could overflow it
+constexpr int EV_STG_LIMIT = (EV_STG - 16) * 8;   // a visit starts with room for two groups of 8 appends
 constexpr int EV_NUM_BARS = 2 * EV_STAGES + 2 * EV_SLOTS + EV_RB;
 constexpr uint32_t EV_IDESC = make_idesc_m128(EV_BN, /*f32 acc*/ 1, /*f16 operands*/ 0);
 constexpr int EV_KP_MAX = 128;
@@ -525,10 +525,13 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                 } else if (__any_sync(0xffffffffu, top > tau)) {
                     // some row of the warp has a candidate in this half tile: narrow down to 8-column groups, and
                     // only there look at single columns
+                    // staging room is checked once per visit (two groups fit) and again before the third and fourth
+                    // group, which are rarely hot in the same visit
+                    int n_hot = 0;
 #pragma unroll
                     for (int gq = 0; gq < 4; ++gq) {
                         if (!__any_sync(0xffffffffu, m8[gq] > tau)) continue;
-                        if (__any_sync(0xffffffffu, saddr - sbase > static_cast<uint32_t>(EV_STG_LIMIT))) {
+                        if ((n_hot == 0 || n_hot >= 2) && __any_sync(0xffffffffu, saddr - sbase > static_cast<uint32_t>(n_hot == 0 ? EV_STG_LIMIT : EV_STG_LIMIT + 64))) {
                             g_cnt = flush_staged(sbase, saddr, row_buf, g_cnt);
                             saddr = sbase;
                             // A list that gets within a tile of its capacity means the starting threshold was far
@@ -536,6 +539,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                             // MMA kernel: it is ~600 instructions that would sit in the middle of the hot loop.)
                             if (g_cnt > EV_TRIGGER) { give_up = true; tau = INFINITY; }
                         }
+                        ++n_hot;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) append_if_above(saddr, __uint_as_float(v[8 * gq + j]), tau, tcol + 8 * gq + j);
                     }
@@ -997,7 +1001,7 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     // k is the smallest rank that leaves >= need full-row columns above the threshold with probability
     // 1 - 1e-3 (a Poisson(need * f) variable reaching k), need = K' + a typical train-item list.  Rows left
     // short fail certification and go to the exact engine.  The sample is sized so that k <= 16 tile maxima.
-    int seed_tiles = 256;
+    int seed_tiles = 512;
     if (const char *env = getenv("CHAOREC_TC_SEED_TILES")) seed_tiles = atoi(env);
     // columns a row needs above its threshold: K, the columns inside the certification window and the slack the
     // approximate order needs (6), plus every train item of the row (a trained model ranks them at the top)
