@@ -8,7 +8,7 @@ from . import _lib
 from .propagate import (CSRGraph, LightGCNConv, bipartite_graph, csr_from_coo, csr_from_sparse_coo,
                         graph_from_edge_index, lightgcn_forward, propagate_mean, resample_masked_graph, spmm)
 from .ranking import (MaskCSR, PositivesCSR, build_mask_csr, build_positives_csr, evaluate, evaluate_full,
-                      gene_ranklist, hit_masks, mask_csr_from_edges, metrics_from_hits, rank_topk)
+                      gene_ranklist, hit_masks, mask_csr_from_edges, metrics_from_hits, rank_topk, rank_topk_sum)
 from .train import GraphedLightGCNStep, bpr_loss, lightgcn_loss, sample_negatives, training_batches
 from .cooccur import user_cooccurrence_topk, user_graph_dict
 from .item_graph import ItemGraph, KnnPattern, knn_graph, normalized_values, original_graph, pattern_matmul
@@ -19,7 +19,7 @@ __all__ = [
     "CSRGraph", "LightGCNConv", "bipartite_graph", "resample_masked_graph", "csr_from_coo", "csr_from_sparse_coo", "graph_from_edge_index",
     "lightgcn_forward", "propagate_mean", "spmm",
     "MaskCSR", "PositivesCSR", "build_mask_csr", "build_positives_csr", "evaluate", "evaluate_full",
-    "gene_ranklist", "hit_masks", "mask_csr_from_edges", "metrics_from_hits", "rank_topk",
+    "gene_ranklist", "hit_masks", "mask_csr_from_edges", "metrics_from_hits", "rank_topk", "rank_topk_sum",
     "GraphedLightGCNStep", "bpr_loss", "lightgcn_loss", "sample_negatives", "training_batches",
     "build_knn_neighbourhood", "get_knn_adj_mat", "knn_laplacian_ones", "knn_self_excluded",
     "knn_sym_laplacian", "knn_topk", "l2_normalize",

@@ -185,9 +185,12 @@ def csr_from_sparse_coo(adj: torch.Tensor) -> CSRGraph:
     if hit is not None and hit[0]() is adj and hit[1] == vals.data_ptr() and hit[2] == vals._version:
         return hit[3]
     g = csr_from_coo(idx[0], idx[1], vals, adj.shape[0], adj.shape[1])
-    if len(_coo_cache) > 64:
-        for k in [k for k, v in _coo_cache.items() if v[0]() is None]:
-            _coo_cache.pop(k, None)
+    # every miss drops the graphs whose adjacency tensor is gone (FREEDOM builds a new masked_adj per epoch; a stale
+    # 100M-edge CSR graph is more than a GB) and keeps at most 8 live entries
+    for k in [k for k, v in _coo_cache.items() if v[0]() is None]:
+        _coo_cache.pop(k, None)
+    while len(_coo_cache) >= 8:
+        _coo_cache.pop(next(iter(_coo_cache)))
     _coo_cache[key] = (weakref.ref(adj), vals.data_ptr(), vals._version, g)
     return g
 
@@ -326,9 +329,10 @@ def graph_from_edge_index(edge_index: torch.Tensor, num_nodes: int) -> CSRGraph:
         dis = src_deg.to(torch.float32).pow(-0.5)
         dis[torch.isinf(dis)] = 0.0     # isolated nodes: never indexed by an edge, keep 0 * scale finite
     g.row_scale, g.col_scale = dis, dis
-    if len(_edge_cache) > 16:
-        for k in [k for k, v in _edge_cache.items() if v[0]() is None]:
-            _edge_cache.pop(k, None)
+    for k in [k for k, v in _edge_cache.items() if v[0]() is None]:
+        _edge_cache.pop(k, None)
+    while len(_edge_cache) >= 8:
+        _edge_cache.pop(next(iter(_edge_cache)))
     _edge_cache[key] = (weakref.ref(edge_index), g, edge_index._version)
     return g
 
@@ -381,6 +385,11 @@ def bipartite_graph(users: torch.Tensor, local_items: torch.Tensor, num_user: in
     n = num_user + num_item
     u = users.to(torch.int64)
     it = local_items.to(torch.int64) + num_user
+    if variant in ("v4", "v5"):
+        # the scipy dok / lil builders keep ONE entry per (user, item) pair however often it occurs in the training
+        # list; the torch COO builders (v1-v3) sum duplicates
+        keys = torch.unique(u * n + it)
+        u, it = keys // n, keys % n
     g = csr_from_coo(torch.cat((u, it)), torch.cat((it, u)), None, n, n)
     dis = torch.empty(n, dtype=torch.float32, device=dev)
     eps = 1e-7 if variant == "v3" else 0.0

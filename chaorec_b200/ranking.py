@@ -35,22 +35,16 @@ def build_mask_csr(user_item_dict: Dict[int, Iterable[int]], num_user: int, num_
                    device: torch.device) -> MaskCSR:
     """``user_item_dict`` {user: [global item ids]} (train items only, dataload.py:30) -> MaskCSR.
     Items outside [num_user, num_user+num_item) are dropped (they cannot index the score matrix)."""
-    users, items = [], []
-    for u, its in user_item_dict.items():
-        u = int(u)
-        if 0 <= u < num_user:
-            arr = np.asarray(list(its), dtype=np.int64) - num_user
-            users.append(np.full(arr.shape, u, dtype=np.int64))
-            items.append(arr)
-    if users:
-        uu = np.concatenate(users)
-        ii = np.concatenate(items)
-        ok = (ii >= 0) & (ii < num_item)
-        keys = np.unique(uu[ok] * num_item + ii[ok])
-        uu, ii = keys // num_item, keys % num_item
-    else:
-        uu = np.zeros(0, dtype=np.int64)
-        ii = np.zeros(0, dtype=np.int64)
+    # no per-user numpy calls: one pass over the dict for the lengths, one flattening pass for the items
+    n = len(user_item_dict)
+    keys_u = np.fromiter(user_item_dict.keys(), dtype=np.int64, count=n)
+    lens = np.fromiter((len(v) for v in user_item_dict.values()), dtype=np.int64, count=n)
+    flat = np.fromiter((x for v in user_item_dict.values() for x in v), dtype=np.int64, count=int(lens.sum()))
+    uu = np.repeat(keys_u, lens)
+    ii = flat - num_user
+    ok = (uu >= 0) & (uu < num_user) & (ii >= 0) & (ii < num_item)
+    keys = np.unique(uu[ok] * num_item + ii[ok])
+    uu, ii = keys // num_item, keys % num_item
     rowptr = np.zeros(num_user + 1, dtype=np.int64)
     np.cumsum(np.bincount(uu, minlength=num_user), out=rowptr[1:])
     return MaskCSR(torch.from_numpy(rowptr).to(device), torch.from_numpy(ii.astype(np.int32)).to(device))
@@ -100,6 +94,20 @@ def rank_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, mask: Optional[Mas
         if stats["pipeline_timeout"][0]:
             stats["pipeline_trace"] = [hex(int(v) & 0xFFFFFFFF) for v in ws[176:256].view(torch.int32).tolist()]
     return (out_idx, out_score) if return_scores else out_idx
+
+
+def rank_topk_sum(user_parts: Sequence[torch.Tensor], item_parts: Sequence[torch.Tensor], mask: Optional[MaskCSR], topk: int,
+                  mask_value: float = 1e-6, id_offset: int = 0, **kw):
+    """Full ranking under a SUM of inner products, ``sum_p user_parts[p] @ item_parts[p].T`` -- the score of the
+    two-tower models (Model/SelfCF.py:213-238: ``u_online . i_target + u_target . i_online``) and of the three-term
+    form (Model/MCLN.py:336-337).  A sum of inner products is the inner product of the concatenated embeddings, so
+    this is one ``rank_topk`` call on ``cat(user_parts, 1)`` / ``cat(item_parts, 1)`` (canonical arithmetic: one
+    fmaf chain over the concatenated width, parts in the given order)."""
+    if len(user_parts) != len(item_parts) or not user_parts:
+        raise RuntimeError("user_parts and item_parts must be non-empty and pair up")
+    u = torch.cat([p.detach().to(torch.float32) for p in user_parts], dim=1)
+    it = torch.cat([p.detach().to(torch.float32) for p in item_parts], dim=1)
+    return rank_topk(u, it, mask, topk, mask_value, id_offset, **kw)
 
 
 # Conversions of the reference's python containers are cached per OBJECT.  Every entry holds a strong reference
@@ -275,17 +283,20 @@ class HostEvalBatch:
 _host_path_cache: Dict[Tuple[int, int], Tuple[torch.cuda.Stream, torch.Tensor]] = {}
 
 
-def evaluate_host_batch(batch, topk: int, device: torch.device, mask_value: float = 1e-6):
+def evaluate_host_batch(batch, topk: int, device: torch.device, mask_value: float = 1e-6, copy: bool = True):
     """Host buffers in, hit masks out: H2D copies, fused ranking, hit masks, D2H -- the part of an
     end-to-end evaluation that runs per rank.  ``batch`` is one ``HostEvalBatch`` or a list of them
     (consecutive user chunks sharing one item table): with a list, the copies of chunk i+1 run on a
     second stream while chunk i is ranked, and the hit masks stream back as they are produced.
-    Returns the hit masks as a pinned int64 host tensor [U_local] (synchronised)."""
+    Returns the hit masks as an int64 host tensor [U_local] (synchronised).  The pinned staging buffer is cached per
+    (device, user count): with ``copy=False`` the returned tensor IS that buffer and is only valid until the next
+    call with the same user count (val followed by test!); the default hands out a copy."""
     chunks = batch if isinstance(batch, (list, tuple)) else [batch]
     lib = _lib.load()
     cur = torch.cuda.current_stream(device)
     total = sum(c.user_emb.shape[0] for c in chunks)
-    key = (device.index, total)
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev_index, total)
     cached = _host_path_cache.get(key)
     if cached is None:     # pinned allocations and stream creation are slow: once per shape
         cached = (torch.cuda.Stream(device=device), torch.empty(total, dtype=torch.int64, pin_memory=True))
@@ -320,4 +331,4 @@ def evaluate_host_batch(batch, topk: int, device: torch.device, mask_value: floa
         off += n
     cur.synchronize()
     copy_stream.synchronize()
-    return hits_host
+    return hits_host.clone() if copy else hits_host

@@ -148,6 +148,12 @@ class GraphedLightGCNStep:
         return loss
 
     def __call__(self, users, pos_items_global, neg_items_global):
+        # the captured kernels have the batch size baked in (static index buffers, 1/B in the loss): a short last
+        # batch of an epoch must go through the eager step or a second captured step of its own size
+        if tuple(users.shape) != tuple(self.users.shape) or tuple(pos_items_global.shape) != tuple(self.pos.shape) \
+                or tuple(neg_items_global.shape) != tuple(self.neg.shape):
+            raise RuntimeError(f"GraphedLightGCNStep was captured for batches of {tuple(self.users.shape)}; got "
+                               f"{tuple(users.shape)} (use training_batches(..., drop_last=True) or an eager step for the tail)")
         self.users.copy_(users, non_blocking=True)
         self.pos.copy_(pos_items_global, non_blocking=True)
         self.neg.copy_(neg_items_global, non_blocking=True)
