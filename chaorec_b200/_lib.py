@@ -10,7 +10,9 @@ from pathlib import Path
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libchaorec_b200.so"
+# (CHAOREC_LIB_PATH: diagnostic builds of the same ABI, e.g. the pipeline-floor variants of scripts/gpu_eval_floor.sh)
+import os as _os
+LIB_PATH = Path(_os.environ["CHAOREC_LIB_PATH"]) if _os.environ.get("CHAOREC_LIB_PATH") else _PKG / "libchaorec_b200.so"
 
 _p = C.c_void_p
 _i64 = C.c_int64

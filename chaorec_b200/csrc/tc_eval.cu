@@ -32,6 +32,17 @@
 #include "engine.cuh"
 #include "tc_ptx.cuh"
 
+// Diagnostic builds only (scripts/gpu_eval_floor.sh): 1 = maxima and threshold test but nothing is listed, 2 = accumulators
+// are read and dropped, 3 = accumulators are not even read.  Results are wrong (every row falls back) -- timing only.
+#ifndef CHAOREC_EV_DEBUG
+#define CHAOREC_EV_DEBUG 0
+#endif
+// Waiting style (measured, scripts/gpu_eval_floor.sh): bit 0 = the MMA issuers poll their barriers, bit 1 = the epilogue
+// warps poll the accumulator-full barrier, before falling back to the suspended bounded wait.
+#ifndef CHAOREC_EV_SPIN
+#define CHAOREC_EV_SPIN 0
+#endif
+
 namespace chaorec {
 namespace {
 using namespace ptx;
@@ -44,18 +55,22 @@ constexpr int EV_STAGES = 8;                      // item-slab ring
 constexpr int EV_STAGE_BYTES = EV_BN * EV_KPAD * 2;
 constexpr int EV_SLOTS = 2 * EV_RB;               // accumulator slots (128 lanes x 64 columns): two private ones per row block
 constexpr int EV_ACC0 = 32 * EV_RB;               // TMEM columns [0,96) hold A: row block rb at 32*rb
-constexpr int EV_CAP = 256;                       // list capacity per (row, slice)
-constexpr int EV_TRIGGER = EV_CAP - 64;           // (a tile appends at most 32 entries to a list)
+constexpr int EV_GCAP = 160;                      // 8-column group records per (row, slice, column half)
+constexpr int EV_REC_WORDS = 12;                  // a record: 8 raw scores, first column, 3 words of padding (16-byte aligned stores)
+constexpr int EV_REC_BYTES = EV_REC_WORDS * 4;
+constexpr int EV_GLIMIT = EV_GCAP - 4;            // (a half-tile visit appends at most 4 records)
+constexpr int EV_MASK_CAP = 256;                  // train items of a row that the approximate cut makes room for
 constexpr int EV_CH = 2;                          // epilogue threads per row: each takes 32 of a tile's 64 columns
 constexpr int EV_EPI_WARPS = 4 * EV_RB * EV_CH;   // warp w: row block w / 8, column half (w / 4) % 2, TMEM lane quarter w % 4
 constexpr int EV_TMA_WARP = EV_EPI_WARPS;         // warp 24
-constexpr int EV_MMA_WARP0 = EV_EPI_WARPS + 1;    // warps 25, 26, 27 issue the MMAs of row blocks 0, 1, 2
-constexpr int EV_THREADS = (EV_EPI_WARPS + 1 + EV_RB) * 32;   // 896 threads -> 72 registers each
-constexpr int EV_SEEDK = 20;                      // tile maxima kept per row in seed mode
+#ifndef CHAOREC_EV_ISSUERS
+#define CHAOREC_EV_ISSUERS 2
+#endif
+constexpr int EV_ISS = CHAOREC_EV_ISSUERS;        // issuing warps per row block (2: one per accumulator slot)
+constexpr int EV_MMA_WARP0 = EV_EPI_WARPS + 1;    // warps 25 .. : issuer w serves row block w / EV_ISS, tiles with parity w % EV_ISS
+constexpr int EV_THREADS = (EV_EPI_WARPS + 1 + EV_RB * EV_ISS) * 32;   // 992 threads -> 64 registers each
+constexpr int EV_SEEDK = 16;                      // tile maxima kept per row in seed mode
 constexpr int EV_SEED_TAB = 128;                  // per-row seed rank is looked up by the row's train-item count
-constexpr int EV_STG = 24;                        // entries of a list's shared-memory staging buffer
-constexpr int EV_STG_BYTES = EV_STG * 8;
-constexpr int EV_STG_LIMIT = (EV_STG - 16) * 8;   // a visit starts with room for two groups of 8 appends
 constexpr int EV_NUM_BARS = 2 * EV_STAGES + 2 * EV_SLOTS + EV_RB;
 constexpr uint32_t EV_IDESC = make_idesc_m128(EV_BN, /*f32 acc*/ 1, /*f16 operands*/ 0);
 constexpr int EV_KP_MAX = 128;
@@ -69,8 +84,8 @@ struct EvalArgs {
     const int64_t *mask_rowptr;   // only the row lengths are used here
     int exclude_self;
     int kp;
-    uint64_t *lists;              // [Ma][n_slices][EV_CH][EV_CAP] raw entries (score bits << 32 | column), 2 KB aligned
-    int32_t *cnt_out;             // [Ma][n_slices][EV_CH]
+    uint32_t *recs;               // [Ma][n_slices][EV_CH][EV_GCAP] group records (EV_REC_WORDS words each), 16-byte aligned
+    int32_t *cnt_out;             // [Ma][n_slices][EV_CH] records written
     float *tau_out;               // [Ma][n_slices][EV_CH] threshold in force at the end of the unit (+inf: row gave up)
     float *seed_scratch;          // seed mode: [gridDim.x][EV_BM][EV_CH][EV_SEEDK] half-tile maxima of the CTA's current unit
     float *tau0;                  // [Ma] starting thresholds: written in seed mode, read in main mode (nullable)
@@ -130,7 +145,7 @@ __device__ __forceinline__ void ev_wait(uint64_t *bar, uint32_t parity, volatile
                 dbg[6] = static_cast<unsigned int>(w >> 32);
                 dbg[7] = threadIdx.x;
 #ifdef CHAOREC_EV_TRACE
-                for (int w2 = 0; w2 < 20; ++w2) dbg[8 + w2] = s_abort[1 + w2];
+                for (int w2 = 0; w2 < 20; ++w2) dbg[8 + w2] = s_abort[3 + w2];
 #endif
             }
             return;
@@ -139,7 +154,9 @@ __device__ __forceinline__ void ev_wait(uint64_t *bar, uint32_t parity, volatile
 }
 
 // Epilogue flavour of the bounded wait, on a precomputed shared-memory address: the common case (phase complete) is a
-// single try_wait and a branch.
+// single try_wait and a branch.  The out-of-line retry loop takes three registers of arguments only (the abort flag and
+// the diagnostics pointer live at fixed shared-memory offsets), so the call site does not drag address arithmetic
+// into the tile loop.
 __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -153,21 +170,52 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t pari
         : "memory");
     return ok != 0;
 }
-__device__ __noinline__ void ev_wait_slow_a(uint32_t bar_addr, uint32_t parity, volatile uint32_t *s_abort, unsigned int *dbg, uint32_t code,
-                                            uint32_t pos) {
+// Non-blocking probe: a warp that polls with it notices a completed phase within a few tens of clocks, where a
+// suspended try_wait takes a few hundred to wake up (the accumulator hand-over is a latency loop: tensor memory holds
+// only ~800 clocks of MMA work at d = 64).
+__device__ __forceinline__ bool mbar_test_wait_a(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_spin_a(uint32_t bar_addr, uint32_t parity, int polls) {
+#pragma unroll 1
+    for (int i = 0; i < polls; ++i)
+        if (mbar_test_wait_a(bar_addr, parity)) return true;
+    return false;
+}
+constexpr int EV_CTRL_OFF = EV_STAGES * EV_STAGE_BYTES + EV_NUM_BARS * 8;   // control words behind the barriers
+struct EvCtrl {
+    uint32_t tmem_base;
+    uint32_t abort_flag;
+    unsigned int *dbg;
+    uint32_t trace[28];
+};
+__device__ __noinline__ void ev_wait_slow_a(uint32_t bar_addr, uint32_t parity, uint32_t code_pos) {
+    extern __shared__ __align__(1024) unsigned char ev_smem_w[];
+    volatile EvCtrl *ctrl = reinterpret_cast<volatile EvCtrl *>(ev_smem_w + EV_CTRL_OFF);
     uint32_t n = 0;
     unsigned long long t0 = 0;
     while (!mbar_try_wait_a(bar_addr, parity)) {
         if ((++n & 63u) != 0u) continue;
-        if (*s_abort) return;
+        if (ctrl->abort_flag) return;
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t0 == 0) t0 = t1;
         if (t1 - t0 > EV_WAIT_NS) {
-            *s_abort = 1u;
+            ctrl->abort_flag = 1u;
+            unsigned int *dbg = ctrl->dbg;
             if (dbg != nullptr && atomicExch(&dbg[0], 1u) == 0u) {
-                dbg[1] = code;
-                dbg[2] = pos;
+                dbg[1] = code_pos >> 20;
+                dbg[2] = code_pos & 0xFFFFFu;
                 dbg[3] = blockIdx.x;
                 dbg[4] = parity;
                 dbg[7] = threadIdx.x;
@@ -190,18 +238,21 @@ __device__ __forceinline__ float max8f(const float (&v)[8]) {
     return m;
 }
 
-// Branch-free conditional append to the row's staging buffer in shared memory (a 32-bit cursor, no global
-// memory descriptor to re-materialise under the predicate): setp + predicated 64-bit store + predicated add.
-__device__ __forceinline__ void append_if_above(uint32_t &saddr, float s, float tau, uint32_t col) {
+// Branch-free conditional store of one 8-column group (raw scores + first column) at the end of the row's record
+// list in global memory: setp + three predicated stores + a predicated pointer bump.  Which of the eight scores
+// beat the threshold is decided by the re-score kernel; the MMA kernel only decides "this group has one".
+__device__ __forceinline__ void store_group_if_above(uint32_t *&p, float m, float tau, const uint32_t *v, uint32_t col) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.gt.f32 p, %1, %2;\n\t"
-        "@p st.shared.v2.u32 [%0], {%3, %4};\n\t"
-        "@p add.u32 %0, %0, 8;\n\t"
+        "@p st.global.v4.u32 [%0], {%3, %4, %5, %6};\n\t"
+        "@p st.global.v4.u32 [%0+16], {%7, %8, %9, %10};\n\t"
+        "@p st.global.u32 [%0+32], %11;\n\t"
+        "@p add.u64 %0, %0, 48;\n\t"
         "}"
-        : "+r"(saddr)
-        : "f"(s), "f"(tau), "r"(col), "r"(__float_as_uint(s))
+        : "+l"(p)
+        : "f"(m), "f"(tau), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(col)
         : "memory");
 }
 
@@ -301,45 +352,33 @@ __device__ __forceinline__ uint32_t select_prefix(LoadKey key_at, int n, int r, 
     return prefix;
 }
 
-// Rare paths of the epilogue, kept out of line so that the tile loop stays small.
-// (1) Move every lane's staged entries to the end of its global list; returns the new list length.
-__device__ __forceinline__ int flush_staged(uint32_t sbase, uint32_t saddr, uint64_t *row_buf, int g_cnt) {
-    const int n = static_cast<int>((saddr - sbase) >> 3);
-#pragma unroll 1
-    for (int i = 0; i < n; ++i) {
-        uint64_t e;
-        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(e) : "r"(sbase + 8u * static_cast<uint32_t>(i)) : "memory");
-        row_buf[g_cnt + i] = e;
-    }
-    return g_cnt + n;
-}
 template <bool SEED>
 __global__ void __launch_bounds__(EV_THREADS, 1)
 tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
     extern __shared__ __align__(1024) unsigned char ev_smem[];
     unsigned char *ring = ev_smem;
-    unsigned char *stg_all = ev_smem + EV_STAGES * EV_STAGE_BYTES;     // [24 warps][32 lanes][EV_STG] staged entries
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stg_all + EV_EPI_WARPS * 32 * EV_STG_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ev_smem + EV_STAGES * EV_STAGE_BYTES);
     uint64_t *full_bar = bars;                              // [EV_STAGES] item slab landed
-    uint64_t *empty_bar = bars + EV_STAGES;                 // [EV_STAGES] both issuers' MMAs on the slab retired
+    uint64_t *empty_bar = bars + EV_STAGES;                 // [EV_STAGES] all issuers' MMAs on the slab retired
     // Every row block owns two accumulator slots (2*rb, 2*rb+1) and alternates between them: tile g of the CTA
     // uses slot 2*rb + (g & 1), barrier phase g >> 1.  (A first version shared six slots between four row blocks;
     // a warp could then be waiting for its row block's NEXT use of a slot while the other row block's use in
     // between had not happened yet -- one parity bit cannot tell those apart -- and, worse, a slot was held until
     // the slowest warp of ANOTHER row block had read it, which serialised MMA and filter.)
     uint64_t *tfull_bar = bars + 2 * EV_STAGES;             // [EV_SLOTS]  accumulator slot complete
-    uint64_t *tempty_bar = tfull_bar + EV_SLOTS;            // [EV_SLOTS]  the four warps of the row block have read it
+    uint64_t *tempty_bar = tfull_bar + EV_SLOTS;            // [EV_SLOTS]  the eight warps of the row block have read it
     uint64_t *afull_bar = tempty_bar + EV_SLOTS;            // [EV_RB]     A rows of the unit are in tensor memory
-    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + EV_NUM_BARS);
-    volatile uint32_t *s_abort = tmem_base_smem + 1;
-    volatile uint32_t *s_trace = s_abort + 1;          // [20] (debug builds)
+    EvCtrl *ctrl = reinterpret_cast<EvCtrl *>(ev_smem + EV_CTRL_OFF);
+    volatile uint32_t *s_abort = &ctrl->abort_flag;
+    volatile uint32_t *s_trace = ctrl->trace;          // (debug builds)
     (void)s_trace;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        *s_abort = 0u;
+        ctrl->abort_flag = 0u;
+        ctrl->dbg = a.dbg;
         for (int s = 0; s < EV_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], EV_RB);
@@ -349,13 +388,16 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
             mbar_init(&tempty_bar[s], 4 * EV_CH);
         }
         for (int s = 0; s < EV_RB; ++s) mbar_init(&afull_bar[s], 4 * EV_CH);
+#ifdef CHAOREC_EV_XCOMMIT
+        for (int s = 0; s < EV_RB; ++s) mbar_init(reinterpret_cast<uint64_t *>(ctrl->trace + 4 + 2 * s), 1);
+#endif
         mbar_fence_init();
     }
-    if (warp == EV_MMA_WARP0) tmem_alloc(tmem_base_smem, 512);
+    if (warp == EV_MMA_WARP0) tmem_alloc(&ctrl->tmem_base, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_base_smem;
+    const uint32_t tmem_base = ctrl->tmem_base;
     const int n_units = a.n_row_tiles * a.n_slices;
     if (warp == EV_TMA_WARP) {
         // ================= TMA producer: one 64-item x 64-element fp16 slab per tile =================
@@ -380,11 +422,15 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
             }
         }
     } else if (warp >= EV_MMA_WARP0) {
-        // ================= MMA issuers: one warp per row block =================
-        const int rb = warp - EV_MMA_WARP0;
-        int stage = 0;
-        uint32_t phase = 0, uphase = 0;
-        int g = 0;                                           // tiles issued by this CTA so far
+        // ================= MMA issuers =================
+        // A converged warp dispatches one 128x64x16 tcgen05.mma every ~50 clocks (profiles/r02_probe_mma_issue_rates.log),
+        // and a tile costs it two barrier probes, four MMAs and two commits: ~500 clocks per tile, which was the floor
+        // of the whole kernel with one issuer per row block.  With two issuers per row block each owns one of the
+        // block's two accumulator slots and takes every other tile.
+        const int rb = (warp - EV_MMA_WARP0) / EV_ISS;
+        const int par = (warp - EV_MMA_WARP0) % EV_ISS;
+        uint32_t uphase = 0;
+        int g0 = 0;                                          // tiles of the CTA before the current unit
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int sl = unit % a.n_slices;
             const int t_lo = sl * a.tiles_per_slice;
@@ -392,13 +438,21 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
             const int n_t = SEED ? a.n_seed_tiles : (t_hi - t_lo);
             ev_wait(&afull_bar[rb], uphase, s_abort, a.dbg, 0x200u | rb, static_cast<uint32_t>(unit));
             uphase ^= 1u;
-            for (int i = 0; i < n_t; ++i, ++g) {
+            for (int i = par; i < n_t; i += EV_ISS) {        // (tile counts are even: the parity of g is the parity of i)
+                const int g = g0 + i;
                 const int slot = 2 * rb + (g & 1);
+                const int stage = g % EV_STAGES;
+                const uint32_t phase = static_cast<uint32_t>((g / EV_STAGES) & 1);
                 EV_TRACE(0x51, i);
                 // both probes are in flight before either result is needed (a completed try_wait still costs ~100 clk)
                 const uint32_t par_e = static_cast<uint32_t>(((g >> 1) & 1) ^ 1);
+#if CHAOREC_EV_SPIN & 1
+                const bool ok_e = mbar_spin_a(smem_u32(&tempty_bar[slot]), par_e, 256);
+                const bool ok_f = mbar_spin_a(smem_u32(&full_bar[stage]), phase, 256);
+#else
                 const bool ok_e = mbar_try_wait(&tempty_bar[slot], par_e);
                 const bool ok_f = mbar_try_wait(&full_bar[stage], phase);
+#endif
                 if (!ok_e) ev_wait(&tempty_bar[slot], par_e, s_abort, a.dbg, 0x300u | slot, static_cast<uint32_t>(i));
                 EV_TRACE(0x52, i);
                 if (!ok_f) ev_wait(&full_bar[stage], phase, s_abort, a.dbg, 0x400u | (rb << 4) | stage, static_cast<uint32_t>(i));
@@ -413,11 +467,14 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                     for (int k = 0; k < 4; ++k) umma_ts(d0, a0 + 8 * k, db + 2 * k, EV_IDESC, k > 0 ? 1u : 0u);
                     umma_commit(&tfull_bar[slot]);
                     umma_commit(&empty_bar[stage]);
+#ifdef CHAOREC_EV_XCOMMIT    // (timing experiment: what does one more tcgen05.commit per tile cost?)
+                    for (int x = 0; x < CHAOREC_EV_XCOMMIT; ++x) umma_commit(reinterpret_cast<uint64_t *>(ctrl->trace + 4 + 2 * rb));
+#endif
                 }
                 __syncwarp();
                 EV_TRACE(0x54, i);
-                if (++stage == EV_STAGES) { stage = 0; phase ^= 1u; }
             }
+            g0 += n_t;
         }
     } else {
         // ================= epilogue: two threads per user row, 32 columns of every tile each =================
@@ -429,11 +486,13 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
         const int row_local = rb * 128 + q * 32 + lane;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const uint32_t sbase = smem_u32(stg_all + (warp * 32 + lane) * EV_STG_BYTES);
-        // tile g of the CTA uses slot 2*rb + (g & 1), phase g >> 1; units have even tile counts
-        const uint32_t bar_full0 = smem_u32(&tfull_bar[2 * rb]), bar_empty0 = smem_u32(&tempty_bar[2 * rb]);
-        const uint32_t taddr0 = lane_base + EV_ACC0 + (2 * rb) * EV_BN + h * 32;
-        const bool lane0 = lane == 0;
+        // tile g of the CTA uses slot 2*rb + (g & 1), phase g >> 1; units have even tile counts.  The three addresses
+        // are made opaque to the compiler: left visible, it re-derives them from %tid inside the tile loop (17
+        // instructions per visit in the round-2a build) instead of keeping three registers alive.
+        uint32_t bar_full0 = smem_u32(&tfull_bar[2 * rb]), bar_empty0 = smem_u32(&tempty_bar[2 * rb]);
+        uint32_t taddr0 = lane_base + EV_ACC0 + (2 * rb) * EV_BN + h * 32;
+        uint32_t lane0 = lane == 0 ? 1u : 0u;
+        asm volatile("" : "+r"(bar_full0), "+r"(bar_empty0), "+r"(taddr0), "+r"(lane0));
         uint32_t spar = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int rt = unit / a.n_slices, sl = unit % a.n_slices;
@@ -469,41 +528,58 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
             float pend = -INFINITY;                           // seed mode: maximum of the pair's first half tile
             float tau = INFINITY;
             bool give_up = false;
-            int r_keep = 0, g_cnt = 0;                        // g_cnt: entries already in the global list
-            uint32_t saddr = sbase;                           // staging cursor
-            uint64_t *row_buf = nullptr;
+            uint32_t *rec_base = nullptr, *rec_p = nullptr, *rec_limit = nullptr;
             if (SEED) {
 #pragma unroll
                 for (int s = 0; s < EV_SEEDK; ++s) tk[s] = -INFINITY;
             } else {
-                r_keep = a.kp + (a.exclude_self ? 1 : 0);
-                if (row_ok && a.mask_rowptr != nullptr) {
-                    const int64_t len = a.mask_rowptr[row + 1] - a.mask_rowptr[row];
-                    r_keep += (len < EV_CAP) ? static_cast<int>(len) : EV_CAP;
-                }
-                // a row whose kept set leaves no room for a tile of appends (a user with hundreds of train
-                // items) is not pre-filtered at all: it goes to the exact engine
-                give_up = !row_ok || (r_keep + 32 > EV_TRIGGER);
+                // A row with more train items than the seed table covers (a user with hundreds of them) is not
+                // pre-filtered at all: it goes to the exact engine.
+                give_up = !row_ok;
+                if (row_ok && a.mask_rowptr != nullptr) give_up = (a.mask_rowptr[row + 1] - a.mask_rowptr[row]) >= EV_SEED_TAB;
                 // Any starting threshold is safe: "every unlisted column scored <= the threshold in force when
                 // it was seen" holds either way, and a row left with too few candidates fails certification.
                 if (!give_up) tau = a.tau0 ? a.tau0[row] : -INFINITY;
-                row_buf = a.lists + ((static_cast<size_t>(row_ok ? row : 0) * a.n_slices + sl) * EV_CH + h) * EV_CAP;
+                rec_base = a.recs + ((static_cast<size_t>(row_ok ? row : 0) * a.n_slices + sl) * EV_CH + h) * (EV_GCAP * EV_REC_WORDS);
+                rec_p = rec_base;
+                rec_limit = rec_base + EV_GLIMIT * EV_REC_WORDS;
             }
             // One visit = one half tile.  The loop is unrolled over the row block's two accumulator slots (tile counts
             // are even), so barrier / TMEM addresses are loop constants and the phase parity flips once per pair.
             auto visit = [&](const uint32_t bar_full, const uint32_t bar_empty, const uint32_t taddr, const int i, const uint32_t tcol) {
-                if (!mbar_try_wait_a(bar_full, spar)) ev_wait_slow_a(bar_full, spar, s_abort, a.dbg, 0x500u | (warp << 4), static_cast<uint32_t>(i));
+#if CHAOREC_EV_SPIN & 2
+                if (!mbar_spin_a(bar_full, spar, 64))
+#else
+                if (!mbar_try_wait_a(bar_full, spar))
+#endif
+                    ev_wait_slow_a(bar_full, spar, (0x500u << 20) | (static_cast<uint32_t>(i) & 0xFFFFFu));
                 tc_fence_after();
                 uint32_t v[32];
                 __syncwarp();
+#if CHAOREC_EV_DEBUG == 3
+                (void)taddr;                                  // pipeline floor: no accumulator reads at all
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+#else
                 tmem_ld32(taddr, v);
                 tmem_ld_wait();
+#endif
                 // the scores are in registers: hand the slot back BEFORE filtering
                 tc_fence_before();
                 __syncwarp();
-                if (lane0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_empty) : "memory");
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p;\n\t"
+                    "setp.ne.u32 p, %1, 0;\n\t"
+                    "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t"
+                    "}" ::"r"(bar_empty), "r"(lane0)
+                    : "memory");
                 // (zero padding beyond Nb exists in the last column tiles only; those columns score exactly 0 and, if
                 // a row lists them, the re-score kernel drops them like any other invalid column)
+#if CHAOREC_EV_DEBUG >= 2
+                (void)tcol;                                   // accumulator reads, no filter
+                return;
+#endif
                 float m8[4];
 #pragma unroll
                 for (int gq = 0; gq < 4; ++gq) m8[gq] = max8(v + 8 * gq);
@@ -522,26 +598,21 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                             tk[s] = hi;
                         }
                     }
-                } else if (__any_sync(0xffffffffu, top > tau)) {
-                    // some row of the warp has a candidate in this half tile: narrow down to 8-column groups, and
-                    // only there look at single columns
-                    // staging room is checked once per visit (two groups fit) and again before the third and fourth
-                    // group, which are rarely hot in the same visit
-                    int n_hot = 0;
+                } else if (__any_sync(0xffffffffu, top > tau) && CHAOREC_EV_DEBUG != 1) {   // (debug 1: maxima and test only)
+                    // Some row of the warp has a candidate in this half tile.  No narrowing down to columns here (that
+                    // cost ~45 instructions per hot group for the whole warp, with one lane doing useful work): every
+                    // lane stores the 8-column groups whose maximum beats its threshold as they are, under a predicate.
+                    // (one group is hot in a typical hot visit: the other three cost a vote and a branch each)
 #pragma unroll
-                    for (int gq = 0; gq < 4; ++gq) {
-                        if (!__any_sync(0xffffffffu, m8[gq] > tau)) continue;
-                        if ((n_hot == 0 || n_hot >= 2) && __any_sync(0xffffffffu, saddr - sbase > static_cast<uint32_t>(n_hot == 0 ? EV_STG_LIMIT : EV_STG_LIMIT + 64))) {
-                            g_cnt = flush_staged(sbase, saddr, row_buf, g_cnt);
-                            saddr = sbase;
-                            // A list that gets within a tile of its capacity means the starting threshold was far
-                            // too low for this row: the row is handed to the exact engine.  (No compaction inside the
-                            // MMA kernel: it is ~600 instructions that would sit in the middle of the hot loop.)
-                            if (g_cnt > EV_TRIGGER) { give_up = true; tau = INFINITY; }
-                        }
-                        ++n_hot;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) append_if_above(saddr, __uint_as_float(v[8 * gq + j]), tau, tcol + 8 * gq + j);
+                    for (int gq = 0; gq < 4; ++gq)
+                        if (__any_sync(0xffffffffu, m8[gq] > tau)) store_group_if_above(rec_p, m8[gq], tau, v + 8 * gq, tcol + 8 * gq);
+                    // A list that gets within a visit of its capacity means the starting threshold was far too low for
+                    // this row: the row is handed to the exact engine.  (Lists are far shorter than 2 GB: the low
+                    // words of the two pointers decide.)
+                    if (static_cast<int32_t>(static_cast<uint32_t>(reinterpret_cast<uintptr_t>(rec_p)) -
+                                             static_cast<uint32_t>(reinterpret_cast<uintptr_t>(rec_limit))) > 0) {
+                        give_up = true;
+                        tau = INFINITY;
                     }
                 }
             };
@@ -583,13 +654,10 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                     a.tau0[row] = vsel;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(EV_EPI_WARPS * 32) : "memory");     // scratch may be overwritten now
-            } else {
-                g_cnt = flush_staged(sbase, saddr, row_buf, g_cnt);
-                if (row_ok) {
-                    const size_t o = (static_cast<size_t>(row) * a.n_slices + sl) * EV_CH + h;
-                    a.cnt_out[o] = give_up ? 0 : g_cnt;
-                    a.tau_out[o] = give_up ? INFINITY : tau;
-                }
+            } else if (row_ok) {
+                const size_t o = (static_cast<size_t>(row) * a.n_slices + sl) * EV_CH + h;
+                a.cnt_out[o] = give_up ? 0 : static_cast<int32_t>((rec_p - rec_base) / EV_REC_WORDS);
+                a.tau_out[o] = give_up ? INFINITY : tau;
             }
         }
     }
@@ -600,7 +668,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
 }
 
 constexpr size_t ev_smem_bytes() {
-    return static_cast<size_t>(EV_STAGES) * EV_STAGE_BYTES + static_cast<size_t>(EV_EPI_WARPS) * 32 * EV_STG_BYTES + EV_NUM_BARS * 8 + 64 + 128;
+    return static_cast<size_t>(EV_CTRL_OFF) + sizeof(EvCtrl) + 64;
 }
 
 // ---- fp32 -> scaled fp16 operand copies -----------------------------------------------------------------
@@ -672,8 +740,8 @@ struct RescoreArgs {
     const float *B;
     int64_t Ma, Nb;
     int D, K, n_slices, kp;
-    const uint64_t *lists;     // [Ma][n_slices][EV_CAP]   (n_slices = column slices x threads per row)
-    const int32_t *cnt;        // [Ma][n_slices]
+    const uint32_t *recs;      // [Ma][n_slices][EV_GCAP] group records (n_slices = column slices x threads per row)
+    const int32_t *cnt;        // [Ma][n_slices] records per list
     const float *tau;          // [Ma][n_slices]
     const float *a_norm;       // [Ma] scaled row norms (upper bounds)
     const float *a_scale;      // [Ma] 2^ea
@@ -696,38 +764,67 @@ struct RescoreArgs {
 constexpr int kRescoreWarps = 4;
 
 __global__ void __launch_bounds__(kRescoreWarps * 32) rescore_lists_kernel(const RescoreArgs a, const int keys_per_warp) {
-    extern __shared__ __align__(16) unsigned char rs_smem[];   // [warps][keys_per_warp] keys, then [warps][256] histogram
+    extern __shared__ __align__(16) unsigned char rs_smem[];   // [warps][keys_per_warp] keys, [warps][256] histogram, [warps][EV_SEED_TAB] train items, [warps] key counts
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = static_cast<int64_t>(blockIdx.x) * kRescoreWarps + wib;
     if (row >= a.Ma) return;
     uint64_t *keys = reinterpret_cast<uint64_t *>(rs_smem) + static_cast<size_t>(wib) * keys_per_warp;
     uint32_t *hist = reinterpret_cast<uint32_t *>(reinterpret_cast<uint64_t *>(rs_smem) + static_cast<size_t>(kRescoreWarps) * keys_per_warp) + wib * 256;
-    // ---- gather the row's lists (all column slices)
-    int n = 0;
+    int32_t *mask_s = reinterpret_cast<int32_t *>(hist - wib * 256 + kRescoreWarps * 256) + wib * EV_SEED_TAB;   // the row's train items
+    int *n_keys = reinterpret_cast<int *>(mask_s - wib * EV_SEED_TAB + kRescoreWarps * EV_SEED_TAB) + wib;
+    // ---- gather the row's records (all column slices and halves): the scores above the list's threshold become keys.
+    // A lane takes whole records (two 16-byte loads + the column word, all independent), so a typical row -- ~50
+    // records per list -- is two rounds of loads per list; the order of `keys` is irrelevant (they are ranked below).
     float tmain = -INFINITY;        // every valid column outside `keys` has approximate score <= tmain
     bool bad = *a.abort_flag != 0u;
+    if (lane == 0) *n_keys = 0;
+    __syncwarp();
     for (int s = 0; s < a.n_slices; ++s) {
         const size_t o = static_cast<size_t>(row) * a.n_slices + s;
         const int c = a.cnt[o];
         const float t = a.tau[o];
         if (!(t < INFINITY)) bad = true;
         tmain = fmaxf(tmain, t);
-        const uint64_t *src = a.lists + o * EV_CAP;
-        for (int i = lane; i < c; i += 32) keys[n + i] = key_of_raw(src[i]);
-        n += c;
+        const uint32_t *src = a.recs + o * (EV_GCAP * EV_REC_WORDS);
+#pragma unroll 2
+        for (int r = lane; r < c; r += 32) {
+            const uint32_t *rec = src + r * EV_REC_WORDS;
+            const uint4 x0 = __ldcs(reinterpret_cast<const uint4 *>(rec));
+            const uint4 x1 = __ldcs(reinterpret_cast<const uint4 *>(rec) + 1);
+            const uint32_t col0 = __ldcs(rec + 8);
+            const uint32_t sc[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            int hits = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hits += (__uint_as_float(sc[j]) > t) ? 1 : 0;
+            int pos = atomicAdd(n_keys, hits);          // one reservation per record (it has one hit, rarely two)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (__uint_as_float(sc[j]) > t) {
+                    if (pos < keys_per_warp) keys[pos] = make_key(__uint_as_float(sc[j]), col0 + j);
+                    ++pos;
+                }
+            }
+        }
     }
+    __syncwarp();
+    int n = *n_keys;
+    if (n > keys_per_warp) { bad = true; n = keys_per_warp; }
     int64_t m_lo = 0;
     int nm_all = 0;
     if (a.mask_rowptr != nullptr) {
         m_lo = a.mask_rowptr[row];
         nm_all = static_cast<int>(a.mask_rowptr[row + 1] - m_lo);
     }
+    // (rows with EV_SEED_TAB or more train items were never pre-filtered: they are `bad` already)
+    if (nm_all >= EV_SEED_TAB) bad = true;
     uint64_t kth = 0ull;
     bool ok = false;
     if (!bad) {
+        // the row's sorted train items: one coalesced read, then every look-up is a shared-memory binary search
+        for (int t = lane; t < nm_all; t += 32) mask_s[t] = a.mask_col[m_lo + t];
         __syncwarp();
         // ---- cut to the r_keep best by approximate score (no sort), then drop invalid columns
-        const int r_keep = a.kp + (a.exclude_self ? 1 : 0) + (nm_all < EV_CAP ? nm_all : EV_CAP);
+        const int r_keep = a.kp + (a.exclude_self ? 1 : 0) + (nm_all < EV_MASK_CAP ? nm_all : EV_MASK_CAP);
         uint32_t prefix = 0u;
         if (n > 64 && n > r_keep + 1) {
             prefix = select_prefix([&](int i) { return keys[i]; }, n, r_keep, lane, hist);
@@ -745,10 +842,10 @@ __global__ void __launch_bounds__(kRescoreWarps * 32) rescore_lists_kernel(const
                 int lo = 0, hi = nm_all;                      // binary search in the row's sorted train items
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
-                    const int32_t mc = a.mask_col[m_lo + mid];
+                    const int32_t mc = mask_s[mid];
                     if (mc < col) lo = mid + 1; else hi = mid;
                 }
-                if (lo < nm_all && a.mask_col[m_lo + lo] == col) v = false;
+                if (lo < nm_all && mask_s[lo] == col) v = false;
             }
             const unsigned bm = __ballot_sync(0xffffffffu, v);
             __syncwarp();
@@ -760,7 +857,7 @@ __global__ void __launch_bounds__(kRescoreWarps * 32) rescore_lists_kernel(const
         while (P < m) P <<= 1;
         for (int t = m + lane; t < P; t += 32) keys[t] = 0ull;
         __syncwarp();
-        warp_sort_desc(keys, P, lane);
+        warp_sort_desc_fast(keys, P, lane);
         int n_cand = m;
         if (m > a.kp) {                                       // only the kp best valid candidates are re-scored
             tmain = fmaxf(tmain, key_score(keys[a.kp]));
@@ -814,13 +911,13 @@ __global__ void __launch_bounds__(kRescoreWarps * 32) rescore_lists_kernel(const
         for (int t = n_cand + lane; t < P2; t += 32) {
             uint64_t key = 0ull;
             if (t < n_cand + nm) {
-                const int32_t mc = a.mask_col[m_lo + (t - n_cand)];
+                const int32_t mc = mask_s[t - n_cand];
                 if (mc >= 0 && mc < a.Nb) key = make_key(a.mask_value, static_cast<uint32_t>(mc));
             }
             keys[t] = key;
         }
         __syncwarp();
-        warp_sort_desc(keys, P2, lane);
+        warp_sort_desc_fast(keys, P2, lane);
         // ---- certification: a valid column outside the candidate set has approximate (scaled) score <= tmain,
         // hence canonical score <= (tmain + eps') * 2^(ea+eb); the exact top-K is final iff its K-th score is
         // strictly above that.  (The power-of-two factors are exact; eps' is rounded up.)
@@ -910,7 +1007,7 @@ size_t tc_eval_workspace_bytes(int64_t Ma, int64_t Nb, int D) {
     n += al256(static_cast<size_t>(Nb) * EV_KPAD * 2);                  // B fp16
     n += 2 * al256(static_cast<size_t>(Ma) * 4) + 256;                  // A norms and scales, B stats
     n += al256(static_cast<size_t>(Ma) * 4);                            // starting thresholds
-    n += 2048 + al256(static_cast<size_t>(Ma) * slices * EV_CH * EV_CAP * 8);   // candidate lists (2 KB aligned)
+    n += 2048 + al256(static_cast<size_t>(Ma) * slices * EV_CH * EV_GCAP * EV_REC_BYTES);   // group records
     n += 2 * al256(static_cast<size_t>(Ma) * slices * EV_CH * 4);       // list lengths, final thresholds
     n += al256(static_cast<size_t>(sm_count()) * EV_BM * EV_CH * EV_SEEDK * 4);   // seed pass: half-tile maxima of a unit
     n += al256(static_cast<size_t>(Ma) * 4);                            // fallback row list
@@ -938,7 +1035,7 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     float *b_stats = reinterpret_cast<float *>(ws); ws += 256;
     float *tau0 = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
     ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ws) + 2047) & ~static_cast<uintptr_t>(2047));
-    uint64_t *lists = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * EV_CH * EV_CAP * 8);
+    uint32_t *recs = reinterpret_cast<uint32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * EV_CH * EV_GCAP * EV_REC_BYTES);
     int32_t *cnt = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * EV_CH * 4);
     float *tau = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * EV_CH * 4);
     float *seed_scratch = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(sm_count()) * EV_BM * EV_CH * EV_SEEDK * 4);
@@ -986,7 +1083,7 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     t.mask_rowptr = e.mask_rowptr;
     t.exclude_self = e.exclude_self;
     t.kp = kp;
-    t.lists = lists; t.cnt_out = cnt; t.tau_out = tau; t.tau0 = nullptr;
+    t.recs = recs; t.cnt_out = cnt; t.tau_out = tau; t.tau0 = nullptr;
     t.dbg = counters + 36;
     t.seed_scratch = seed_scratch;
 
@@ -1040,7 +1137,7 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
 
     RescoreArgs r{};
     r.A = e.A; r.B = e.B; r.Ma = e.Ma; r.Nb = e.Nb; r.D = e.d; r.K = e.K; r.n_slices = slices * EV_CH; r.kp = kp;
-    r.lists = lists; r.cnt = cnt; r.tau = tau; r.a_norm = a_norm; r.a_scale = a_scale; r.b_stats = b_stats;
+    r.recs = recs; r.cnt = cnt; r.tau = tau; r.a_norm = a_norm; r.a_scale = a_scale; r.b_stats = b_stats;
     // |s~' - s'| <= gamma |a'||b'|max in scaled units, against the CANONICAL fp32 score s':
     //   fp16 rounding of both operands      2 * 2^-11 + 2^-22
     //   fp16 subnormal flush (|x'| < 2^-14)  2^-24 * sqrt(64) relative to |a'||b'|max (both >= 1)
@@ -1053,9 +1150,10 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     r.fallback_rows = fb_rows; r.fallback_seeds = fb_seeds; r.fallback_count = counters + 16;
     r.abort_flag = counters + 36;
     {
-        int keys_per_warp = 512;                                   // a power of two >= all listed entries of a row
-        while (keys_per_warp < slices * EV_CH * EV_CAP) keys_per_warp <<= 1;
-        const size_t rs_smem = static_cast<size_t>(kRescoreWarps) * (keys_per_warp * 8 + 256 * 4);
+        // keys of a row: a power of two; a row that lists more (far more than any sane threshold produces) goes to
+        // the exact engine
+        const int keys_per_warp = 512;
+        const size_t rs_smem = static_cast<size_t>(kRescoreWarps) * (keys_per_warp * 8 + 256 * 4 + EV_SEED_TAB * 4 + 4);
         ce = cudaFuncSetAttribute(rescore_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rs_smem));
         if (ce != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
         rescore_lists_kernel<<<static_cast<unsigned>((e.Ma + kRescoreWarps - 1) / kRescoreWarps), kRescoreWarps * 32, rs_smem, stm>>>(

@@ -130,5 +130,50 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t *s, int P, int lane) {
     }
 }
 
+// The same network for exactly 64 keys held two per lane (element e = lane + 32 r): compare-exchanges go through
+// shuffles instead of shared memory -- ~300 warp instructions against ~730 for the shared-memory form.
+__device__ __forceinline__ void warp_sort64_desc_regs(uint64_t &k0, uint64_t &k1, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+        // direction of the length-k run element e sits in: bit k of e; for k = 32 that bit is r, not a lane bit
+        const bool desc0 = (k == 32) ? true : ((lane & k) == 0);
+        const bool desc1 = (k == 32) ? false : desc0;
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool lower = (lane & j) == 0;
+            const uint64_t o0 = __shfl_xor_sync(0xffffffffu, k0, j);
+            const uint64_t o1 = __shfl_xor_sync(0xffffffffu, k1, j);
+            k0 = (lower == desc0) ? (k0 > o0 ? k0 : o0) : (k0 < o0 ? k0 : o0);
+            k1 = (lower == desc1) ? (k1 > o1 ? k1 : o1) : (k1 < o1 ? k1 : o1);
+        }
+    }
+    // k = 64: descending everywhere; j = 32 pairs the lane's own two elements
+    {
+        const uint64_t hi = k0 > k1 ? k0 : k1, lo = k0 > k1 ? k1 : k0;
+        k0 = hi;
+        k1 = lo;
+    }
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const bool keep_max = (lane & j) == 0;
+        const uint64_t o0 = __shfl_xor_sync(0xffffffffu, k0, j);
+        const uint64_t o1 = __shfl_xor_sync(0xffffffffu, k1, j);
+        k0 = keep_max ? (k0 > o0 ? k0 : o0) : (k0 < o0 ? k0 : o0);
+        k1 = keep_max ? (k1 > o1 ? k1 : o1) : (k1 < o1 ? k1 : o1);
+    }
+}
+// sort P keys in shared memory (descending): through registers when P == 64
+__device__ __forceinline__ void warp_sort_desc_fast(uint64_t *s, int P, int lane) {
+    if (P == 64) {
+        uint64_t k0 = s[lane], k1 = s[lane + 32];
+        warp_sort64_desc_regs(k0, k1, lane);
+        s[lane] = k0;
+        s[lane + 32] = k1;
+        __syncwarp();
+    } else {
+        warp_sort_desc(s, P, lane);
+    }
+}
+
 }  // namespace ptx
 }  // namespace chaorec

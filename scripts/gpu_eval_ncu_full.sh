@@ -19,6 +19,9 @@ torch.cuda.synchronize()
 PY
 KPAT=${1:-tc_eval_kernel}
 SKIP=${2:-1}
-timeout 420 ncu --set full --clock-control none --import-source on -k regex:$KPAT -s $SKIP -c 1 -f -o gpurun_out/prof_eval python /tmp/evalonce.py > gpurun_out/prof_eval.log 2>&1
-tail -3 gpurun_out/prof_eval.log
-ls -la gpurun_out/prof_eval.ncu-rep
+OUT=${3:-prof_eval}
+timeout 420 ncu --set full --clock-control none --import-source on -k regex:$KPAT -s $SKIP -c 1 -f -o gpurun_out/$OUT python /tmp/evalonce.py > gpurun_out/$OUT.log 2>&1
+tail -3 gpurun_out/$OUT.log
+ncu -i gpurun_out/$OUT.ncu-rep --page raw --csv > gpurun_out/${OUT}_raw.csv 2>/dev/null
+ncu -i gpurun_out/$OUT.ncu-rep --page source --csv > gpurun_out/${OUT}_source.csv 2>/dev/null
+ls -la gpurun_out/$OUT.ncu-rep
