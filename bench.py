@@ -44,9 +44,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--legs", default="eval,propagate,knn,train")
+    ap.add_argument("--legs", default="eval,propagate,knn,train,seam")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every workload (debug only; marks the line)")
     ap.add_argument("--cpu-sample-users", type=int, default=None)
+    ap.add_argument("--cpu-legs", action="store_true", help="run the host-side baseline legs even at --scale < 1")
     return ap.parse_args()
 
 
@@ -105,6 +106,127 @@ def shard_eval_job(job, lo, hi, n_chunks=1):
 
 
 # --------------------------------------------------------------------------------------------
+# parity gates (outside every timed region; a mismatch aborts the run -- no number without parity)
+# --------------------------------------------------------------------------------------------
+
+
+class ParityError(SystemExit):
+    pass
+
+
+def parity_fail(what, detail):
+    raise ParityError(f"PARITY GATE FAILED ({what}): {detail} -- no bench line is printed for a wrong result")
+
+
+def gate_eval(job, lo, hi, dev, ue, ie, mask, world, n_users=8192):
+    """A seeded sample of this rank's users + EVERY row the tensor engine handed to the exact engine, re-derived by the
+    oracle (oracle/canon.c: canonical fmaf chain, mask value, lowest-index tie-break): ids and score bits must be equal;
+    the hit masks / metrics of the same users must equal the oracle's restatement of utils.gene_metrics."""
+    import chaorec_b200 as cb
+    from chaorec_b200 import _lib
+    from chaorec_b200.ranking import metrics_from_hits
+    from oracle.canon_py import Canon
+    from oracle import ref_ops
+    canon = Canon()
+    U, I, K = job["U"], job["I"], job["K"]
+    n_local = hi - lo
+    st = {}
+    idx, sc = cb.rank_topk(ue, ie, mask, K, 1e-6, U, return_scores=True, stats=st)
+    g = torch.Generator().manual_seed(97 + lo)
+    take = min(max(n_users // world, 64), n_local)
+    sample = torch.randperm(n_local, generator=g)[:take]
+    fb = st.get("fallback_row_ids")
+    n_fb = int(fb.numel()) if fb is not None else 0
+    if fb is not None and n_fb:
+        sample = torch.unique(torch.cat((sample, fb[:4096])))
+    sample = sample.sort()[0]
+    rp, mc = job["mask_rowptr"], job["mask_col"]
+    gl = sample + lo
+    lens = (rp[gl + 1] - rp[gl])
+    sub_rp = torch.zeros(sample.numel() + 1, dtype=torch.int64)
+    sub_rp[1:] = torch.cumsum(lens, 0)
+    sub_col = torch.cat([mc[int(rp[u]):int(rp[u + 1])] for u in gl.tolist()]) if sample.numel() else mc[:0]
+    t0 = time.perf_counter()
+    cidx, csc = canon.score_mask_topk(job["user"][gl].numpy(), job["item"].numpy(), sub_rp.numpy(), sub_col.numpy(), 1e-6, K, id_offset=U)
+    t_oracle = time.perf_counter() - t0
+    sd = sample.to(dev)
+    got_idx, got_sc = idx[sd].cpu().numpy(), sc[sd].cpu().numpy()
+    bad_rows = int((got_idx != cidx).any(axis=1).sum())
+    bad_scores = int((got_sc.view(np.uint32) != csc.view(np.uint32)).any(axis=1).sum())
+    if bad_rows or bad_scores:
+        parity_fail("eval", f"{bad_rows} of {sample.numel()} sampled users differ in top-{K} ids, {bad_scores} in score bits")
+    # metrics of the sampled users: reference python loop (restated) vs hit-mask kernel + host reduction
+    rows = np.empty(sample.numel(), dtype=object)
+    pos = job["pos"][gl].tolist()
+    for j in range(sample.numel()):
+        rows[j] = [j] + pos[j]
+    ks = [5, 10, 20]
+    want = ref_ops.gene_metrics(rows, torch.from_numpy(cidx), ks)
+    got = cb.evaluate(None, rows, torch.from_numpy(got_idx), ks, device=dev)
+    if any(got[k][n] != want[k][n] for k in ks for n in got[k]):
+        parity_fail("eval metrics", f"{got} != {want}")
+    return dict(users_checked=int(sample.numel()), fallback_rows=st.get("fallback_rows"), fallback_rows_checked=min(n_fb, 4096),
+                ids="bit-exact", scores="bit-exact", metrics="identical (==)", oracle="oracle/canon.c + ref_ops.gene_metrics",
+                oracle_s=round(t_oracle, 2)), st
+
+
+def fp64_reference_chain(graph, dis, x0, L):
+    """Independent fp64 product chain + layer mean on the device: torch.sparse (cuSPARSE) CSR @ dense in float64 on the
+    SAME CSR pattern with the edge weights d^-1/2[r] d^-1/2[c] formed in float64 (the checker, not the product)."""
+    n = graph.M
+    counts = graph.rowptr[1:] - graph.rowptr[:-1]
+    rows = torch.repeat_interleave(torch.arange(n, device=x0.device), counts)
+    d64 = dis.double()
+    vals = d64[rows] * d64[graph.col.long()]
+    del rows
+    adj = torch.sparse_csr_tensor(graph.rowptr, graph.col.long(), vals, size=(n, graph.N))
+    x = x0.double()
+    acc = x.clone()
+    for _ in range(L):
+        x = torch.sparse.mm(adj, x)
+        acc += x
+    return acc / (L + 1), adj
+
+
+def gate_propagate(res, ref, what, tol=1e-5):
+    err = float((res.double() - ref).abs().max() / ref.abs().max())
+    if not (err <= tol):
+        parity_fail(what, f"max|delta|/max|ref| = {err:.3e} > {tol:g}")
+    return err
+
+
+def gate_knn(x, k, lo, hi, val, idx, n_windows=3, width=24):
+    """A few row windows of this rank's range re-derived by the oracle (canonical normalisation + fmaf chain):
+    neighbour ids and similarity bits must be equal."""
+    from oracle.canon_py import Canon
+    canon = Canon()
+    xh = x.cpu().numpy()
+    g = torch.Generator().manual_seed(11 + lo)
+    n = hi - lo
+    starts = sorted({0, max(n - width, 0), *[int(v) for v in torch.randint(0, max(n - width, 1), (n_windows,), generator=g)]})
+    checked = 0
+    for s0 in starts:
+        r0, r1 = lo + s0, min(lo + s0 + width, hi)
+        cval, cidx = canon.knn_cosine_topk(xh, k, 0, r0, r1)
+        gi, gv = idx[s0:s0 + (r1 - r0)].cpu().numpy(), val[s0:s0 + (r1 - r0)].cpu().numpy()
+        if not np.array_equal(gi, cidx) or not np.array_equal(gv.view(np.uint32), cval.view(np.uint32)):
+            parity_fail("knn", f"rows [{r0},{r1}) of a {xh.shape} table differ from the oracle")
+        checked += r1 - r0
+    return dict(rows_checked=checked, ids="bit-exact", values="bit-exact", oracle="oracle/canon.c")
+
+
+def profile_traffic(key):
+    """DRAM bytes per launch of the named kernel from the ncu --set full captures of this round
+    (profiles/r02_traffic.json, written by scripts/write_traffic_json.py together with the commit it was taken at)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    e = d.get(key)
+    return (e.get("dram_bytes") if e else None), dict(file="profiles/r02_traffic.json", commit=d.get("commit"), entry=key)
+
+
+# --------------------------------------------------------------------------------------------
 # clocks sampling during the timed region
 # --------------------------------------------------------------------------------------------
 
@@ -113,13 +235,17 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
+    """nvidia-smi in loop mode, started BEFORE the warm-up (its own start-up takes longer than a short timed region);
+    every line is time-stamped on arrival and `stop(t0, t1)` reports the samples that fall inside the timed window
+    (all samples taken under load since the start if the window is shorter than two sampling periods)."""
+
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -128,9 +254,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.monotonic(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -138,9 +264,13 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        rows = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1)]
+        window = "timed region"
+        if len(rows) < 2:
+            rows, window = [r for (_, r) in self.rows], "warm-up + timed region (timed region shorter than two samples)"
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -152,7 +282,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # --------------------------------------------------------------------------------------------
@@ -211,7 +341,7 @@ def run_eval_leg(args, dev, rank, world, peaks):
     U, I, d, K = job["U"], job["I"], job["d"], job["K"]
     lo, hi = cdist.shard_range(U, world, rank)
     batch = shard_eval_job(job, lo, hi)
-    e2e_chunks = shard_eval_job(job, lo, hi, n_chunks=2 if (hi - lo) >= 400_000 else 1)
+    e2e_chunks = shard_eval_job(job, lo, hi, n_chunks=2 if (hi - lo) >= 50_000 else 1)
     n_local = hi - lo
     ks = [5, 10, 20]
 
@@ -223,8 +353,7 @@ def run_eval_leg(args, dev, rank, world, peaks):
     hits = torch.empty(n_local, dtype=torch.int64, device=dev)
     l2buf = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
-    st = {}
-    cb.rank_topk(ue, ie, mask, K, 1e-6, U, stats=st)            # which engine, how many rows fell back
+    parity, st = gate_eval(job, lo, hi, dev, ue, ie, mask, world)   # aborts on any mismatch; also: engine, fallback rows
 
     def one_step(timed):
         flush_l2(l2buf)
@@ -242,14 +371,15 @@ def run_eval_leg(args, dev, rank, world, peaks):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(dev.index)
+    sampler.start()
     for _ in range(args.warmup):
         one_step(False)
     barrier()
-    sampler = ClockSampler(dev.index)
-    sampler.start()
+    t_w0 = time.monotonic()
     evs = [one_step(True) for _ in range(args.steps)]
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_w0, time.monotonic())
     t_total = sum(e0.elapsed_time(e2) for e0, _, e2 in evs) * 1e-3
     t_rank_kernel = sum(e0.elapsed_time(e1) for e0, e1, _ in evs) * 1e-3 / args.steps
     tt = torch.tensor([t_total, t_rank_kernel], dtype=torch.float64, device=dev)
@@ -261,10 +391,12 @@ def run_eval_leg(args, dev, rank, world, peaks):
     # ---- end-to-end leg (host buffers in, metrics out) ------------------------------------------
     n_pos_all = np.full(U, job["pos"].shape[1], dtype=np.int32)
 
+    shard_sizes = [cdist.shard_range(U, world, r)[1] - cdist.shard_range(U, world, r)[0] for r in range(world)]
+
     def e2e_step():
-        h = evaluate_host_batch(e2e_chunks, K, dev)          # pinned host tensor, synchronised
+        h = evaluate_host_batch(e2e_chunks, K, dev, copy=False)   # pinned host tensor, synchronised (consumed before the next call)
         if world > 1:
-            all_h = cdist.gather_to_rank0(h.to(dev))
+            all_h = cdist.gather_to_rank0(h.to(dev), sizes=shard_sizes)
             if rank != 0:
                 return None
             hh = all_h.cpu().numpy()
@@ -290,14 +422,15 @@ def run_eval_leg(args, dev, rank, world, peaks):
     achieved = flops / t_rank_kernel / 1e12
     tensor = st.get("engine") == "tensor"
     if tensor:
-        roof = dict(kernel="tc_candidates_kernel (tcgen05 bf16 pre-filter; time includes bf16 conversion, fp32 re-score + "
-                           "certification and the exact fallback launch)", bound="tensor", achieved=achieved,
+        traffic, traffic_src = profile_traffic("tc_eval_kernel_main") if (world == 1 and args.scale == 1.0) else (None, None)
+        roof = dict(kernel="tc_eval_kernel<false> (tcgen05 fp16 pre-filter); `achieved` divides by the time of the WHOLE ranking "
+                           "chain: fp16 conversion, seed pass, main pass, fp32 re-score + certification, exact fallback launch",
+                    bound="tensor", achieved=achieved,
                     peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops"],
-                    # dram__bytes_read+write of the main tc_candidates_kernel<true> launch at this exact workload on 1 GPU,
-                    # from the ncu --set full capture profiles/r01_final_tc_eval_summary.csv (1.39 GB read + 1.65 GB written)
-                    traffic=(3.05e9 if (world == 1 and args.scale == 1.0) else None),
+                    frac_of_sustained_peak=(achieved / peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None,
+                    traffic=traffic, traffic_source=traffic_src,
                     tmem_read_tbps_measured=probe_tmem_read(dev),
-                    peak_source=peaks["source"] + " (bf16 dense burst)", algorithmic_flops_per_launch=flops,
+                    peak_source=peaks["source"] + " (bf16 dense burst; fp16 and bf16 tcgen05 rates are equal)", algorithmic_flops_per_launch=flops,
                     kernel_ms=t_rank_kernel * 1e3, fallback_rows=st.get("fallback_rows"),
                     fp32_fma_peak_tflops_measured=fp32_peak)
     else:
@@ -310,8 +443,8 @@ def run_eval_leg(args, dev, rank, world, peaks):
         value=value, ms_per_step=t_total / args.steps * 1e3, clocks=clocks,
         e2e=dict(value=e2e_value, unit="users/s", h2d_bytes_per_step=batch.h2d_bytes(), d2h_bytes_per_step=n_local * 8,
                  includes="H2D of embeddings+mask+positives, rank kernel, hits kernel, D2H hit masks, gather, host fp64 metrics"),
-        roofline=roof, engine=st.get("engine"),
-        gpu_launches=(11 if tensor else 2) * args.steps,   # to_bf16 x2, max_reduce, gather_rows, tc_candidates x2, rescore, rank_topk x2 + slice_merge (fallback rows), topk_hits
+        roofline=roof, engine=st.get("engine"), parity=dict(eval=parity),
+        gpu_launches=(10 if tensor else 2) * args.steps,   # absmax, to_f16 x2, tc_eval seed + main, rescore_lists, rank_topk x3 + slice_merge (fallback rows), topk_hits
         config=dict(workload="full-rank top-20 eval, 1M users x 200k items, d=64 (BASELINE configs[3])", users=U, items=I,
                     d=d, topk=K, mask_items_per_user=EVAL_CFG["mask_per_user"], sharding=f"users/{world}",
                     l2="flushed between steps (192 MiB write)", scale=args.scale),
@@ -360,6 +493,20 @@ def gpu_zipf_graph(cfg, scale, dev):
     return U, I, keys // I, keys % I
 
 
+def build_full_graph(tu, ti, U, I, dev):
+    """The whole symmetric normalized adjacency on one GPU (the N = 1 leg, and the reference rows of the N > 1 gates)."""
+    import chaorec_b200 as cb
+    from chaorec_b200 import _lib
+    n = U + I
+    graph = cb.csr_from_coo(torch.cat((tu, ti + U)), torch.cat((ti + U, tu)), None, n, n)
+    lib = _lib.load()
+    dis = torch.empty(n, dtype=torch.float32, device=dev)
+    _lib.check(lib.chaorec_degree_inv_sqrt(_lib.ptr(graph.rowptr), n, 0.0, _lib.ptr(dis), _lib.stream_ptr(dev)), "deg")
+    graph.row_scale = graph.col_scale = dis
+    graph.symmetric = True
+    return graph, dis
+
+
 def run_propagate_leg(args, dev, rank, world, peaks):
     import chaorec_b200 as cb
     if world > 1:
@@ -368,18 +515,47 @@ def run_propagate_leg(args, dev, rank, world, peaks):
     U, I, tu, ti = gpu_zipf_graph(cfg, args.scale, dev)
     n, d, L = U + I, cfg["d"], cfg["L"]
     E = int(tu.numel())
-    row = torch.cat((tu, ti + U))
-    col = torch.cat((ti + U, tu))
+    graph, dis = build_full_graph(tu, ti, U, I, dev)
     del tu, ti
-    graph = cb.csr_from_coo(row, col, None, n, n)
-    del row, col
-    from chaorec_b200 import _lib
-    lib = _lib.load()
-    dis = torch.empty(n, dtype=torch.float32, device=dev)
-    _lib.check(lib.chaorec_degree_inv_sqrt(_lib.ptr(graph.rowptr), n, 0.0, _lib.ptr(dis), _lib.stream_ptr(dev)), "deg")
-    graph.row_scale = graph.col_scale = dis
-    graph.symmetric = True
     x0 = torch.randn(n, d, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 0.1
+    # ---- parity gate: the whole table against an fp64 CSR product chain (all rows, not a sample)
+    res = cb.propagate_mean(graph, x0, L)
+    ref, adj64 = fp64_reference_chain(graph, dis, x0, L)
+    err = gate_propagate(res, ref, "propagate")
+    parity = dict(rows_checked=n, rel_err=err, tol=1e-5, reference="torch.sparse CSR fp64 chain on the device (cuSPARSE), all rows")
+    del res, ref
+    # ---- informal library column: the same layer through torch.sparse.mm (fp32 CSR, cuSPARSE) on this GPU
+    lib_ms = None
+    try:
+        adj32 = torch.sparse_csr_tensor(adj64.crow_indices(), adj64.col_indices(), adj64.values().float(), size=adj64.shape)
+        del adj64
+        for _ in range(2):
+            torch.sparse.mm(adj32, x0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            torch.sparse.mm(adj32, x0)
+        e1.record()
+        torch.cuda.synchronize()
+        lib_ms = e0.elapsed_time(e1) / 3
+        # ---- CPU baseline leg (BASELINE.md plan of record): ONE layer of torch.sparse.mm on the host cores, COO as the
+        # reference builds it (Model/FREEDOM.py:73-109) and CSR
+        cpu_leg = None
+        if rank == 0 and args.scale == 1.0 or args.cpu_legs:
+            coo = adj32.to_sparse_coo()
+            coo = torch.sparse_coo_tensor(coo.indices().cpu(), coo.values().cpu(), tuple(coo.shape), is_coalesced=True)
+            xc = x0.cpu()
+            t0 = time.perf_counter(); torch.sparse.mm(coo, xc); t_coo = time.perf_counter() - t0
+            csr = coo.to_sparse_csr()
+            t0 = time.perf_counter(); torch.sparse.mm(csr, xc); t_csr = time.perf_counter() - t0
+            cpu_leg = dict(coo_ms_per_layer=t_coo * 1e3, csr_ms_per_layer=t_csr * 1e3, cores=torch.get_num_threads(), kind="reference operator",
+                           sample="one layer (of 3) of torch.sparse.mm(adj, x) on the host, same graph and table")
+            del coo, csr, xc
+        del adj32
+    except Exception as exc:       # the library column is informal: never fail the bench for it
+        cpu_leg = dict(error=f"{type(exc).__name__}: {exc}"[:200])
+    torch.cuda.empty_cache()
     for _ in range(args.warmup):
         cb.propagate_mean(graph, x0, L)
     torch.cuda.synchronize()
@@ -395,17 +571,17 @@ def run_propagate_leg(args, dev, rank, world, peaks):
     nnz = 2 * E
     bytes_layer = nnz * (4 + 4 * d) + n * (4 * d + 8)          # 260 B/edge + 264 B/node
     achieved = bytes_layer * L / t / 1e9
+    prop_traffic, prop_traffic_src = profile_traffic("spmm_layer") if args.scale == 1.0 else (None, None)
     return dict(metric="GCN propagate edges/s", value=nnz * L / t, unit="edges/s", ms_per_step=t * 1e3,
                 config=dict(workload="3-layer normalized-adjacency propagation + layer mean (BASELINE configs[4] shape)",
                             users=U, items=I, edges=E, nnz_sym=nnz, d=d, layers=L, hub_rows=graph.n_hub,
                             hub_chunks=graph.n_hub_chunks, l2="inputs (2.7 GB table, 0.8 GB indices) exceed L2", scale=args.scale),
                 roofline=dict(kernel="spmm_rows_kernel<16,1,64,20> (+hub kernels)", bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"],
                               unit="GB/s", frac=achieved / peaks["hbm_gbs"],
-                              # ncu dram bytes per layer at this workload (profiles/r01_final_spmm_*_summary.csv): rows
-                              # kernel 21.2 GB read + 5.3 GB written, hub-chunk kernel 20.6 GB read + 0.2 GB written
-                              # -> 47.3 GB against 52.9 GB algorithmic (L2 absorbs the popular item rows)
-                              traffic=(47.3e9 if args.scale == 1.0 else None), peak_source=peaks["source"],
+                              # traffic: ncu dram bytes of one layer's kernels (rows + hub-chunk + hub-finish) at this workload
+                              traffic=prop_traffic, traffic_source=prop_traffic_src, peak_source=peaks["source"],
                               algorithmic_bytes_per_layer=bytes_layer),
+                parity=parity, library_torch_sparse_mm_csr_ms_per_layer=lib_ms, cpu_baseline=cpu_leg,
                 gpu_launches=(1 + (2 if graph.n_hub else 0)) * L * args.steps)
 
 
@@ -442,7 +618,13 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
     x0 = torch.randn(n, d, device=dev, generator=gen) * 0.1
     xu0 = x0[shard.u_lo:shard.u_hi].contiguous()
     xi0 = x0[U:].contiguous()
-    del x0
+    # ---- parity gate: this rank's user rows and ALL item rows against the single-GPU product of the same graph
+    full_graph, _ = build_full_graph(tu, ti, U, I, dev)
+    ref = cb.propagate_mean(full_graph, x0, L)
+    acc_u, acc_i = cdist.propagate_mean_bipartite(shard, xu0, xi0, L)
+    err_b = max(gate_propagate(acc_u, ref[shard.u_lo:shard.u_hi].double(), f"sharded propagate (bipartite, rank {rank})"),
+                gate_propagate(acc_i, ref[U:].double(), f"sharded propagate (bipartite item rows, rank {rank})"))
+    del acc_u, acc_i, x0
     t = timed(lambda: cdist.propagate_mean_bipartite(shard, xu0, xi0, L))
     del shard, xu0, xi0
     torch.cuda.empty_cache()
@@ -462,6 +644,16 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
     graph.row_scale = dis_perm[rank * part.block:(rank + 1) * part.block].contiguous()
     graph.col_scale = dis_perm
     x0 = torch.randn(part.n_padded, d, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 0.1
+    # ---- parity gate: this rank's block against the single-GPU product (node order -> permuted order)
+    ref = part.permute_rows(cb.propagate_mean(full_graph, part.unpermute_rows(x0).contiguous(), L))
+    blk = cdist.propagate_mean_sharded(graph, part, x0, L)
+    err_c = gate_propagate(blk, ref[rank * part.block:(rank + 1) * part.block].double(), f"sharded propagate (row-cyclic, rank {rank})")
+    del ref, blk, full_graph
+    errs = torch.tensor([err_b, err_c], dtype=torch.float64, device=dev)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    parity = dict(bipartite_rel_err=float(errs[0]), row_cyclic_rel_err=float(errs[1]), tol=1e-5, rows_checked="every rank: all rows of its shard",
+                  reference="single-GPU propagate_mean of the same graph (itself gated against the fp64 chain at N=1)")
+    torch.cuda.empty_cache()
     t_cyclic = timed(lambda: cdist.propagate_mean_sharded(graph, part, x0, L))
     nnz = 2 * E
     bytes_layer = nnz * (4 + 4 * d) + n * (4 * d + 8)
@@ -474,7 +666,7 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
                             exchanged_bytes_per_layer=I * d * 4),
                 roofline=dict(kernel="spmm_rows_kernel<16,1,64,20> (+hub kernels)", bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"],
                               unit="GB/s per GPU", frac=achieved / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"]),
-                gpu_launches=None)
+                parity=parity, gpu_launches=None)
 
 
 def run_knn_leg(args, dev, rank, world, peaks):
@@ -490,7 +682,8 @@ def run_knn_leg(args, dev, rank, world, peaks):
         if name == "v_feat":
             x = torch.relu(x)
         kst = {}
-        cb.knn_topk(x, cfg["k"], row_range=(lo, hi), stats=kst)
+        val, idx = cb.knn_topk(x, cfg["k"], row_range=(lo, hi), stats=kst)
+        parity = gate_knn(x, cfg["k"], lo, hi, val, idx)           # aborts on any mismatch
         for _ in range(max(1, args.warmup - 1)):
             cb.knn_topk(x, cfg["k"], row_range=(lo, hi))
         torch.cuda.synchronize()
@@ -508,18 +701,118 @@ def run_knn_leg(args, dev, rank, world, peaks):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t = float(tt[0])
         flops = 2.0 * N * N * D
-        cpu_ms = None
-        if world == 1 and name == "t_feat":
-            # the reference's own form (Model/FREEDOM.py:111-128: normalise, dense sim, topk) on the host cores
+        cpu_ms = cpu_b_ms = lib_ms = None
+        if world == 1 and rank == 0:
+            # the reference's own forms on the host cores: conv A (Model/FREEDOM.py:111-128: normalise, dense sim, topk)
+            # for both modalities, conv B (Model/LATTICE.py:46-75: build_sim, topk, scatter, symmetric Laplacian) for t_feat
             from oracle import ref_ops
             xc = x.cpu()
             t0 = time.perf_counter()
             ref_ops.knn_conv_a(xc, cfg["k"])
             cpu_ms = (time.perf_counter() - t0) * 1e3
-        out[name] = dict(value=N / t, unit="item rows/s", ms=t * 1e3, cpu_reference_ms=cpu_ms, D=D, N=N, k=cfg["k"], tflops=flops / t / 1e12,
+            if name == "t_feat":
+                t0 = time.perf_counter()
+                ref_ops.knn_conv_b(xc, cfg["k"])
+                cpu_b_ms = (time.perf_counter() - t0) * 1e3
+            # informal library column: the same reference form with torch's CUDA kernels (cuBLAS fp32 GEMM + topk)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for it_ in range(2):
+                if it_ == 1:
+                    e0.record()
+                xn = x / torch.norm(x, p=2, dim=-1, keepdim=True)
+                torch.topk(torch.mm(xn, xn.t()), cfg["k"], dim=-1)
+            e1.record()
+            torch.cuda.synchronize()
+            lib_ms = e0.elapsed_time(e1)
+            del xn
+        out[name] = dict(value=N / t, unit="item rows/s", ms=t * 1e3, cpu_reference_ms=cpu_ms, cpu_reference_conv_b_ms=cpu_b_ms,
+                         library_torch_cuda_mm_topk_ms=lib_ms, cpu_cores=torch.get_num_threads(),
+                         D=D, N=N, k=cfg["k"], tflops=flops / t / 1e12,
                          frac_of_bf16_tensor_peak=flops / t / 1e12 / peaks["bf16_tflops"], engine=kst.get("engine"),
-                         fallback_rows=kst.get("fallback_rows"))
+                         fallback_rows=kst.get("fallback_rows"), parity=parity)
     return dict(metric="kNN graph item rows/s", config=dict(workload="cosine kNN graph, clothing-shaped (BASELINE configs[2])"), **out)
+
+
+SEAM_CFGS = [dict(name="C1 baby-shaped", U=19_445, I=7_050, E=160_000, d=64, L=3, seed=20260),
+             dict(name="C2 sports-shaped", U=35_598, I=18_357, E=296_337, d=64, L=3, seed=20261)]
+
+
+def run_seam_leg(args, dev, rank, world, peaks):
+    """The drop-in seam exactly as INTEGRATION.md §1 wires it, on the reference's own small configs (BASELINE configs[0]
+    and [1]): python `user_item_dict`, object-array val/test rows, LightGCN forward, then
+        rank = types.MethodType(cb.gene_ranklist, model)(topk=50); cb.evaluate(model, val, rank, ks); cb.evaluate(model, test, rank, ks)
+    (train_and_evaluate.py:656-659) -- cold (first call: container conversion, H2D, workspace allocation) and warm
+    (conversions cached per object), beside the oracle port of the reference doing the same on the host cores.  Parity gate:
+    every metric identical (==) and the ranklists equal to the reference's stable-sorted form."""
+    import types
+    import chaorec_b200 as cb
+    from chaorec_b200 import ranking
+    from oracle import ref_ops
+    out = {}
+    ks = [5, 10, 20]
+    for cfg in SEAM_CFGS:
+        U, I, d, L = int(cfg["U"] * args.scale), int(cfg["I"] * args.scale), cfg["d"], cfg["L"]
+        tu, ti = ref_ops.synth_interactions(U, I, int(cfg["E"] * args.scale), cfg["seed"])
+        held = ref_ops.synth_holdout(U, I, tu, ti, 4, cfg["seed"] + 1)
+        _, uid, val = ref_ops.to_reference_formats(U, tu, ti, held[:, :2])
+        _, _, test = ref_ops.to_reference_formats(U, tu, ti, held[:, 2:])
+        ei_cpu = ref_ops.symmetrise_edges(torch.stack((tu, ti + U), 1).numpy())
+        uw, iw = ref_ops.xavier_embeddings(U, d, 1), ref_ops.xavier_embeddings(I, d, 2)
+        # ---- reference port on the host cores: forward + gene_ranklist + evaluate x2
+        t0 = time.perf_counter()
+        res_cpu = ref_ops.lightgcn_forward(uw, iw, ei_cpu, L)
+        t_fwd_cpu = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        rank_cpu = ref_ops.gene_ranklist(res_cpu, U, I, uid, topk=50)
+        mv = ref_ops.gene_metrics(val, rank_cpu, ks)
+        mt = ref_ops.gene_metrics(test, rank_cpu, ks)
+        t_eval_cpu = time.perf_counter() - t0
+        # ---- ours through the seam
+        uwd, iwd, ei = uw.to(dev), iw.to(dev), ei_cpu.to(dev)
+        cb.lightgcn_forward(uwd, iwd, ei, L)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = cb.lightgcn_forward(uwd, iwd, ei, L)
+        torch.cuda.synchronize()
+        t_fwd = time.perf_counter() - t0
+        same_fwd = float((res.cpu() - res_cpu).abs().max() / res_cpu.abs().max())
+        if not same_fwd <= 1e-5:
+            parity_fail("seam forward " + cfg["name"], f"rel err {same_fwd}")
+        # the evaluation seam is fed the SAME embedding bits as the reference port (its own forward output), so that
+        # the two ranklists are comparable item by item
+        model = types.SimpleNamespace(result=res_cpu.to(dev), num_user=U, num_item=I, user_item_dict=uid)
+        model.gene_ranklist = types.MethodType(cb.gene_ranklist, model)
+        times = []
+        for rep in range(3):
+            if rep == 0:
+                ranking.clear_caches()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rk = model.gene_ranklist(topk=50)
+            gv = cb.evaluate(model, val, rk, ks)
+            gt = cb.evaluate(model, test, rk, ks)
+            times.append(time.perf_counter() - t0)
+        # ---- parity: (1) ranklist == the oracle's canonical one, bit for bit; (2) metrics == the reference loop on it;
+        # (3) reported, not gated: equality with the torch.matmul/topk port (whose summation order is the BLAS build's)
+        from oracle.canon_py import Canon
+        rp = np.zeros(U + 1, dtype=np.int64)
+        np.cumsum(np.bincount(tu.numpy(), minlength=U), out=rp[1:])
+        cidx, _ = Canon().score_mask_topk(res_cpu[:U].numpy(), res_cpu[U:].numpy(), rp, ti.numpy().astype(np.int32), 1e-6, 50, id_offset=U)
+        if not np.array_equal(rk.numpy(), cidx):
+            parity_fail("seam " + cfg["name"], "gene_ranklist differs from the oracle's canonical ranklist")
+        cv, ct = ref_ops.gene_metrics(val, torch.from_numpy(cidx), ks), ref_ops.gene_metrics(test, torch.from_numpy(cidx), ks)
+        if any(gv[k][n] != cv[k][n] or gt[k][n] != ct[k][n] for k in ks for n in gv[k]):
+            parity_fail("seam " + cfg["name"], f"metrics differ: {gv} / {cv}")
+        port_equal = all(gv[k][n] == mv[k][n] and gt[k][n] == mt[k][n] for k in ks for n in gv[k])
+        rows_equal = int((rk == rank_cpu).all(dim=1).sum())
+        out[cfg["name"]] = dict(users=U, items=I, interactions=int(tu.numel()), topk=50,
+                                ours_forward_ms=t_fwd * 1e3, ours_eval_cold_ms=times[0] * 1e3, ours_eval_warm_ms=min(times[1:]) * 1e3,
+                                reference_cpu_forward_ms=t_fwd_cpu * 1e3, reference_cpu_eval_ms=t_eval_cpu * 1e3, cpu_cores=torch.get_num_threads(),
+                                users_per_s_cold=U / times[0], users_per_s_warm=U / min(times[1:]), users_per_s_reference_cpu=U / t_eval_cpu,
+                                parity=dict(ranklist="bit-exact vs oracle/canon.c (top-50, all users)", metrics="identical (==) to the reference loop on that ranklist, val and test, k=5,10,20",
+                                            forward_rel_err=same_fwd, metrics_identical_to_torch_matmul_port=port_equal,
+                                            ranklist_rows_identical_to_torch_topk_port=f"{rows_equal}/{U}"))
+    return dict(metric="drop-in seam: gene_ranklist + evaluate x2 through the reference's python containers", **out)
 
 
 TRAIN_CFG = dict(U=35_598, I=18_357, E=296_337, d=64, L=3, batch=1024, reg=1e-4, seed=20262)
@@ -632,6 +925,9 @@ def main_ours(args):
     if "train" in legs:
         torch.cuda.empty_cache()
         line["train"] = run_train_leg(args, dev, rank, world, peaks)
+    if "seam" in legs and world == 1:
+        torch.cuda.empty_cache()
+        line["seam"] = run_seam_leg(args, dev, rank, world, peaks)
     if rank == 0 and world == 1 and job is not None:
         cpu, _ = run_cpu_baseline_eval(job, args.cpu_sample_users or 131072)       # ~13 s of host work on 16 cores
         line["cpu_baseline"] = cpu

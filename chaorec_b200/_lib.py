@@ -40,6 +40,7 @@ SIGNATURES = {
     "chaorec_bpr_loss_grad_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _i64, _f32, _p, _p, _p]),
     "chaorec_score_mask_topk_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "chaorec_uses_tensor_engine": (C.c_int, [_i64, _i64, _i32, _i32]),
+    "chaorec_score_mask_topk_fallback_rows": (_p, [_p, _i64, _i64, _i32, _i32]),
     "chaorec_score_mask_topk_f32": (C.c_int, [_p, _p, _p, _p, _f32, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _sz,
                                               _p]),
     "chaorec_topk_hits": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _p]),
@@ -56,7 +57,7 @@ SIGNATURES = {
 _lib = None
 
 
-ABI_VERSION = 2      # CHAOREC_ABI_VERSION of include/chaorec_b200.h this binding was written against
+ABI_VERSION = 3      # CHAOREC_ABI_VERSION of include/chaorec_b200.h this binding was written against
 
 
 def load() -> C.CDLL:

@@ -43,5 +43,6 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
 bool tc_eval_supported(int64_t Ma, int64_t Nb, int D, int K);
 size_t tc_eval_workspace_bytes(int64_t Ma, int64_t Nb, int D);
 int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes, cudaStream_t stm);
+const int32_t *tc_eval_fallback_rows(void *workspace, int64_t Ma, int64_t Nb);
 
 }  // namespace chaorec

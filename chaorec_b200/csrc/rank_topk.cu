@@ -621,6 +621,11 @@ extern "C" int chaorec_uses_tensor_engine(int64_t rows, int64_t cols, int32_t d,
     return use_tensor_engine(rows, cols, d, K) ? 1 : 0;
 }
 
+extern "C" const int32_t *chaorec_score_mask_topk_fallback_rows(void *workspace, int64_t U, int64_t I, int32_t d, int32_t K) {
+    if (!workspace || d > 64 || !use_tensor_engine(U, I, d, K)) return nullptr;
+    return tc_eval_fallback_rows(workspace, U, I);
+}
+
 extern "C" size_t chaorec_score_mask_topk_workspace_bytes(int64_t U, int64_t I, int32_t d, int32_t K) {
     size_t n = rank_workspace_bytes(U, d);
     if (tc_supported(U, I, d, K)) n = max_size(n, tc_workspace_bytes(U, I, d));

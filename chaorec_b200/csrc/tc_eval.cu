@@ -1022,27 +1022,61 @@ bool tc_eval_supported(int64_t Ma, int64_t Nb, int D, int K) {
            Nb < 0x7FFFFFC0LL && ev_encode_fn() != nullptr;
 }
 
+namespace {
+// The one place that knows how the workspace is laid out (the launcher and the fallback-row query both use it).
+struct EvalWs {
+    int slices;
+    unsigned int *counters;
+    __half *a16, *b16;
+    float *a_norm, *a_scale, *b_stats, *tau0;
+    uint32_t *recs;
+    int32_t *cnt;
+    float *tau, *seed_scratch;
+    int32_t *fb_rows;
+    uint64_t *fb_seeds;
+    void *rank_ws;
+};
+EvalWs carve_eval_ws(void *workspace, int64_t Ma, int64_t Nb) {
+    EvalWs w{};
+    const int slices = tc_eval_choose_slices(Ma, Nb);
+    w.slices = slices;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    w.counters = reinterpret_cast<unsigned int *>(ws); ws += 256;
+    w.a16 = reinterpret_cast<__half *>(ws); ws += al256(static_cast<size_t>(Ma) * EV_KPAD * 2);
+    w.b16 = reinterpret_cast<__half *>(ws); ws += al256(static_cast<size_t>(Nb) * EV_KPAD * 2);
+    w.a_norm = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(Ma) * 4);
+    w.a_scale = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(Ma) * 4);
+    w.b_stats = reinterpret_cast<float *>(ws); ws += 256;
+    w.tau0 = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(Ma) * 4);
+    ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ws) + 2047) & ~static_cast<uintptr_t>(2047));
+    w.recs = reinterpret_cast<uint32_t *>(ws); ws += al256(static_cast<size_t>(Ma) * slices * EV_CH * EV_GCAP * EV_REC_BYTES);
+    w.cnt = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(Ma) * slices * EV_CH * 4);
+    w.tau = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(Ma) * slices * EV_CH * 4);
+    w.seed_scratch = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(sm_count()) * EV_BM * EV_CH * EV_SEEDK * 4);
+    w.fb_rows = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(Ma) * 4);
+    w.fb_seeds = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(Ma) * 8);
+    w.rank_ws = ws;
+    return w;
+}
+}  // namespace
+
+// Device pointer of the list of rows the last tc_eval_launch on this workspace handed to the exact engine (their
+// number is the uint32 at byte offset 64 of the workspace).
+const int32_t *tc_eval_fallback_rows(void *workspace, int64_t Ma, int64_t Nb) { return carve_eval_ws(workspace, Ma, Nb).fb_rows; }
+
 // A, B: fp32 operands (same pointer allowed).  Computes the exact canonical top-K of every row of A.
 int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes, cudaStream_t stm) {
     if (workspace_bytes < tc_eval_workspace_bytes(e.Ma, e.Nb, e.d)) return CHAOREC_E_WORKSPACE;
-    const int slices = tc_eval_choose_slices(e.Ma, e.Nb);
-    unsigned char *ws = static_cast<unsigned char *>(workspace);
-    unsigned int *counters = reinterpret_cast<unsigned int *>(ws); ws += 256;
-    __half *a16 = reinterpret_cast<__half *>(ws); ws += al256(static_cast<size_t>(e.Ma) * EV_KPAD * 2);
-    __half *b16 = reinterpret_cast<__half *>(ws); ws += al256(static_cast<size_t>(e.Nb) * EV_KPAD * 2);
-    float *a_norm = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
-    float *a_scale = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
-    float *b_stats = reinterpret_cast<float *>(ws); ws += 256;
-    float *tau0 = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
-    ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ws) + 2047) & ~static_cast<uintptr_t>(2047));
-    uint32_t *recs = reinterpret_cast<uint32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * EV_CH * EV_GCAP * EV_REC_BYTES);
-    int32_t *cnt = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * EV_CH * 4);
-    float *tau = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(e.Ma) * slices * EV_CH * 4);
-    float *seed_scratch = reinterpret_cast<float *>(ws); ws += al256(static_cast<size_t>(sm_count()) * EV_BM * EV_CH * EV_SEEDK * 4);
-    int32_t *fb_rows = reinterpret_cast<int32_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 4);
-    uint64_t *fb_seeds = reinterpret_cast<uint64_t *>(ws); ws += al256(static_cast<size_t>(e.Ma) * 8);
-    void *rank_ws = ws;
-    const size_t rank_ws_bytes = workspace_bytes - static_cast<size_t>(ws - static_cast<unsigned char *>(workspace));
+    const EvalWs w = carve_eval_ws(workspace, e.Ma, e.Nb);
+    const int slices = w.slices;
+    unsigned int *counters = w.counters;
+    __half *a16 = w.a16, *b16 = w.b16;
+    float *a_norm = w.a_norm, *a_scale = w.a_scale, *b_stats = w.b_stats, *tau0 = w.tau0, *tau = w.tau, *seed_scratch = w.seed_scratch;
+    uint32_t *recs = w.recs;
+    int32_t *cnt = w.cnt, *fb_rows = w.fb_rows;
+    uint64_t *fb_seeds = w.fb_seeds;
+    void *rank_ws = w.rank_ws;
+    const size_t rank_ws_bytes = workspace_bytes - static_cast<size_t>(static_cast<unsigned char *>(w.rank_ws) - static_cast<unsigned char *>(workspace));
 
     // counters[16] = fallback count (read by the host shim), counters[32] = max |B| bits; b_stats zeroed for atomicMax
     if (cudaMemsetAsync(counters, 0, 256, stm) != cudaSuccess || cudaMemsetAsync(b_stats, 0, 256, stm) != cudaSuccess) {

@@ -43,20 +43,26 @@ def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_to_rank0(local: torch.Tensor, group=None) -> Optional[torch.Tensor]:
-    """Concatenates 1-D/2-D per-rank tensors of uneven length along dim 0 on rank 0."""
+def gather_to_rank0(local: torch.Tensor, group=None, sizes=None) -> Optional[torch.Tensor]:
+    """Concatenates 1-D/2-D per-rank tensors of uneven length along dim 0 on rank 0 (a real gather: only rank 0
+    receives).  ``sizes``: the per-rank lengths when the caller knows them (``shard_range``), which saves the
+    exchange of the lengths."""
     rank, world = world_info()
     if world == 1:
         return local
-    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    if sizes is None:
+        n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        got = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(got, n, group=group)
+        sizes = [int(s.item()) for s in got]
     cap = max(sizes)
-    pad = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad, group=group)
+    if local.shape[0] == cap:
+        pad = local.contiguous()
+    else:
+        pad = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, out, dst=0, group=group)
     if rank != 0:
         return None
     return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)

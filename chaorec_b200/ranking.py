@@ -88,6 +88,11 @@ def rank_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, mask: Optional[Mas
         tensor = bool(lib.chaorec_uses_tensor_engine(U, I, d, int(topk)))
         stats["engine"] = "tensor" if tensor else "exact"
         stats["fallback_rows"] = int(ws[64:68].view(torch.int32).item()) if tensor else 0
+        # which rows (d <= 64 engine only): parity gates re-derive every one of them on the host
+        fb_ptr = lib.chaorec_score_mask_topk_fallback_rows(_lib.ptr(ws), U, I, d, int(topk)) if tensor else None
+        if fb_ptr:
+            off = (int(fb_ptr) - ws.data_ptr()) // 4
+            stats["fallback_row_ids"] = ws.view(torch.int32)[off:off + stats["fallback_rows"]].to(torch.int64).sort()[0].cpu()
         # d <= 64 engine: first time-out record of the MMA pipeline's bounded waits (all zero = healthy; a non-zero
         # flag means every row was recomputed by the exact engine -- correct but slow, see csrc/tc_eval.cu)
         stats["pipeline_timeout"] = [int(v) for v in ws[144:176].view(torch.int32).tolist()] if tensor and d <= 64 else [0] * 8

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CHAOREC_ABI_VERSION 2   /* 2: hub plan arguments of the SpMM entry points, new entry points */
+#define CHAOREC_ABI_VERSION 3   /* 2: hub plan arguments of the SpMM entry points; 3: fallback-row query */
 
 enum {
     CHAOREC_OK = 0,
@@ -174,6 +174,13 @@ size_t chaorec_score_mask_topk_workspace_bytes(int64_t U, int64_t I, int32_t d, 
  * exact engine once the call has completed.
  */
 int chaorec_uses_tensor_engine(int64_t rows, int64_t cols, int32_t d, int32_t K);
+/*
+ * Which rows were re-run by the exact engine: device pointer (inside `workspace`) of an int32 list whose length is
+ * the uint32 at byte offset 64 of the workspace; valid once the chaorec_score_mask_topk_f32 call on that workspace
+ * has completed and until the workspace is reused.  NULL when the shape does not use the d <= 64 tensor engine.
+ * (Diagnostics: parity gates check every such row against the oracle.)
+ */
+const int32_t *chaorec_score_mask_topk_fallback_rows(void *workspace, int64_t U, int64_t I, int32_t d, int32_t K);
 int chaorec_score_mask_topk_f32(const float *user_emb, const float *item_emb, const int64_t *mask_rowptr,
                                 const int32_t *mask_col, float mask_value, int64_t U, int64_t I, int32_t d,
                                 int32_t K, int64_t id_offset, int64_t *out_idx, float *out_score,

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_strings():
     lib = _lib.load()
-    assert lib.chaorec_abi_version() == 2
+    assert lib.chaorec_abi_version() == 3
     assert lib.chaorec_error_string(0) == b"ok"
     for code in (-1, -2, -3, -4, -5):
         assert len(lib.chaorec_error_string(code)) > 4

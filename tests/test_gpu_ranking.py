@@ -180,12 +180,18 @@ def test_million_user_config_sampled_bit_exact(canon):
     mu = torch.arange(U).repeat_interleave(16)
     mi = perm[torch.searchsorted(cdf, torch.rand(mu.numel(), generator=g, dtype=torch.float64)).clamp_(max=I - 1)]
     mask = cb.mask_csr_from_edges(mu.to(dev()), mi.to(dev()), U, I)
-    idx, sc = cb.rank_topk(u.to(dev()), it.to(dev()), mask, K, 1e-6, id_offset=U, return_scores=True)
+    st = {}
+    idx, sc = cb.rank_topk(u.to(dev()), it.to(dev()), mask, K, 1e-6, id_offset=U, return_scores=True, stats=st)
     assert bool((sc[:, 1:] <= sc[:, :-1]).all())
     assert int(idx.min()) >= U and int(idx.max()) < U + I
     srt = torch.sort(idx, dim=1)[0]
     assert bool((srt[:, 1:] != srt[:, :-1]).all())
-    sample = torch.randperm(U, generator=g)[:192].sort()[0]
+    # 2048 seeded users + every row the tensor engine handed to the exact engine
+    sample = torch.randperm(U, generator=g)[:2048]
+    if st.get("fallback_row_ids") is not None:
+        assert st["fallback_rows"] == st["fallback_row_ids"].numel()
+        sample = torch.unique(torch.cat((sample, st["fallback_row_ids"][:2048])))
+    sample = sample.sort()[0]
     rp, col = _csr_np(mask)
     sub_rp = np.zeros(sample.numel() + 1, dtype=np.int64)
     cols = []
@@ -279,3 +285,60 @@ def test_host_batch_path_chunked_equals_single():
     want = cb.evaluate(None, rows, rank, [5, 10, 20])
     got = metrics_from_hits(h3, np.full(job["U"], job["pos"].shape[1], dtype=np.int32), [5, 10, 20])
     assert got == want
+
+
+def test_certification_margin_near_ties(canon, engine):
+    """Columns planted just inside / far outside the certification margin of the tensor engine: a copy of each chosen
+    user's K-th best item scaled by (1 - delta) scores s_K (1 - delta), i.e. it becomes the (K+1)-th best at distance
+    delta * s_K.  delta = 2^-13 is far inside the fp16 pre-filter's error bound (~1e-3 |a||b|): those rows cannot be
+    certified and must be re-run by the exact engine; delta = 0.2 is far outside: those rows stay certified (unless
+    they have a natural near-tie).  The output is bit-exact either way."""
+    U, I, d, K = 1536, 8192, 64, 20
+    u = ref_ops.normal_embeddings(U, d, 301)
+    it = ref_ops.normal_embeddings(I, d, 302)
+    base_idx, base_sc = canon.score_mask_topk(u.numpy(), it.numpy(), None, None, 1e-6, K, 0)
+    it2 = it.clone()
+    near, far = list(range(0, 64)), list(range(64, 128))
+    for r in near + far:
+        assert base_sc[r, K - 1] > 0
+        delta = 2.0 ** -13 if r in near else 0.2
+        it2[I - 1 - r] = it[int(base_idx[r, K - 1])] * (1.0 - delta)
+    st = {}
+    idx, sc = cb.rank_topk(u.to(dev()), it2.to(dev()), None, K, 1e-6, 0, return_scores=True, stats=st)
+    cidx, csc = canon.score_mask_topk(u.numpy(), it2.numpy(), None, None, 1e-6, K, 0)
+    assert np.array_equal(idx.cpu().numpy(), cidx)
+    assert np.array_equal(sc.cpu().numpy().view(np.uint32), csc.view(np.uint32))
+    if engine == "auto":
+        assert st["engine"] == "tensor"
+        fb = set(st["fallback_row_ids"].tolist())
+        assert st["fallback_rows"] == len(fb)
+        assert set(near) <= fb, sorted(set(near) - fb)               # inside the margin: never certified
+        assert len(fb & set(far)) <= 8                                # far outside: certified (natural near-ties aside)
+        assert len(fb) <= len(near) + U // 8
+
+
+def test_sum_of_inner_products_two_tower_and_three_term(canon):
+    """Score-combination variants of gene_ranklist: u.i' + u'.i (Model/SelfCF.py:213-238) and the three-term sum
+    (Model/MCLN.py:336-337) are one ranking call on the concatenated embeddings.  Bit-exact against the oracle's chain
+    over the concatenated width; the reference's own arithmetic (separate fp32 matmuls, then adds) agrees on every row
+    up to near-ties (scores within 1e-6 relative)."""
+    U, I, d, K = 700, 3000, 64, 20
+    tu, ti = ref_ops.synth_interactions(U, I, 6 * U, 41)
+    mask = cb.mask_csr_from_edges(tu.to(dev()), ti.to(dev()), U, I)
+    rp, col = _csr_np(mask)
+    for n_parts in (2, 3):
+        ups = [ref_ops.normal_embeddings(U, d, 50 + p) for p in range(n_parts)]
+        ips = [ref_ops.normal_embeddings(I, d, 60 + p) for p in range(n_parts)]
+        idx, sc = cb.rank_topk_sum([x.to(dev()) for x in ups], [x.to(dev()) for x in ips], mask, K, 1e-6, id_offset=U, return_scores=True)
+        cidx, csc = canon.score_mask_topk(torch.cat(ups, 1).numpy(), torch.cat(ips, 1).numpy(), rp, col, 1e-6, K, id_offset=U)
+        assert np.array_equal(idx.cpu().numpy(), cidx)
+        assert np.array_equal(sc.cpu().numpy().view(np.uint32), csc.view(np.uint32))
+        # the reference's form
+        s = sum(torch.matmul(a, b.t()) for a, b in zip(ups, ips))
+        s[tu, ti] = 1e-6
+        ref_sc, ref_idx = torch.sort(s, dim=1, descending=True, stable=True)
+        assert torch.allclose(sc.cpu(), ref_sc[:, :K], rtol=1e-5, atol=1e-7)
+        same = (idx.cpu() == ref_idx[:, :K] + U).all(dim=1).float().mean()
+        assert float(same) >= 0.995
+    with pytest.raises(RuntimeError):
+        cb.rank_topk_sum([ups[0].to(dev())], [], mask, K)
