@@ -625,8 +625,26 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
     err_b = max(gate_propagate(acc_u, ref[shard.u_lo:shard.u_hi].double(), f"sharded propagate (bipartite, rank {rank})"),
                 gate_propagate(acc_i, ref[U:].double(), f"sharded propagate (bipartite item rows, rank {rank})"))
     del acc_u, acc_i, x0
-    t = timed(lambda: cdist.propagate_mean_bipartite(shard, xu0, xi0, L))
-    del shard, xu0, xi0
+    t_nccl = timed(lambda: cdist.propagate_mean_bipartite(shard, xu0, xi0, L))
+    # ---- the same propagation with the exchange fused into the kernels (peer stores from the SpMM epilogue, owner-side
+    # reduce + store into every table, device-side barriers): gated like the NCCL form, and the headline when available
+    err_f, t = None, t_nccl
+    fused_note = None
+    try:
+        ex = cdist.FusedItemExchange(I, d, dev)
+        fu, fi = cdist.propagate_mean_bipartite_fused(shard, ex, xu0, xi0, L)
+        err_f = max(gate_propagate(fu, ref[shard.u_lo:shard.u_hi].double(), f"sharded propagate (fused exchange, rank {rank})"),
+                    gate_propagate(fi, ref[U:].double(), f"sharded propagate (fused exchange item rows, rank {rank})"))
+        del fu, fi
+        t_fused = timed(lambda: cdist.propagate_mean_bipartite_fused(shard, ex, xu0, xi0, L))
+        t = t_fused
+        del ex
+    except ParityError:
+        raise
+    except Exception as exc:
+        fused_note = f"fused exchange unavailable: {type(exc).__name__}: {exc}"[:300]
+        t_fused = None
+    del ref, shard, xu0, xi0
     torch.cuda.empty_cache()
     # --- generic row-cyclic partition, one all-gather of the whole table per layer ------------------
     part = cdist.CyclicPartition(n, world)
@@ -649,9 +667,10 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
     blk = cdist.propagate_mean_sharded(graph, part, x0, L)
     err_c = gate_propagate(blk, ref[rank * part.block:(rank + 1) * part.block].double(), f"sharded propagate (row-cyclic, rank {rank})")
     del ref, blk, full_graph
-    errs = torch.tensor([err_b, err_c], dtype=torch.float64, device=dev)
+    errs = torch.tensor([err_b, err_c, err_f if err_f is not None else -1.0], dtype=torch.float64, device=dev)
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
-    parity = dict(bipartite_rel_err=float(errs[0]), row_cyclic_rel_err=float(errs[1]), tol=1e-5, rows_checked="every rank: all rows of its shard",
+    parity = dict(bipartite_nccl_rel_err=float(errs[0]), row_cyclic_nccl_rel_err=float(errs[1]),
+                  bipartite_fused_rel_err=(float(errs[2]) if err_f is not None else None), tol=1e-5, rows_checked="every rank: all rows of its shard",
                   reference="single-GPU propagate_mean of the same graph (itself gated against the fp64 chain at N=1)")
     torch.cuda.empty_cache()
     t_cyclic = timed(lambda: cdist.propagate_mean_sharded(graph, part, x0, L))
@@ -659,9 +678,12 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
     bytes_layer = nnz * (4 + 4 * d) + n * (4 * d + 8)
     achieved = bytes_layer * L / t / 1e9 / world
     return dict(metric="GCN propagate edges/s", value=nnz * L / t, unit="edges/s", ms_per_step=t * 1e3,
+                exchange=("fused: SpMM epilogue stores item partials into the owners' inboxes over NVLink, owners reduce and store into every "
+                          "rank's table (no NCCL call per layer)" if t_fused is not None else "NCCL all-reduce of the item partials"),
+                fused_note=fused_note,
+                bipartite_nccl_allreduce=dict(value=nnz * L / t_nccl, unit="edges/s", ms_per_step=t_nccl * 1e3),
                 generic_row_cyclic_allgather=dict(value=nnz * L / t_cyclic, unit="edges/s", ms_per_step=t_cyclic * 1e3),
-                config=dict(workload="3-layer propagation, users sharded and kept local, one NCCL all-reduce of the item "
-                                     "partials [I, d] per layer",
+                config=dict(workload="3-layer propagation, users sharded and kept local, item partials [I, d] exchanged once per layer",
                             users=U, items=I, edges=E, nnz_sym=nnz, d=d, layers=L, world=world, scale=args.scale,
                             exchanged_bytes_per_layer=I * d * 4),
                 roofline=dict(kernel="spmm_rows_kernel<16,1,64,20> (+hub kernels)", bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"],

@@ -33,6 +33,8 @@ __host__ __device__ __forceinline__ int64_t hub_chunk_edges(int64_t deg, int hub
     return per > hub_chunk ? (per + 63) / 64 * 64 : hub_chunk;
 }
 
+constexpr int kMaxPeers = 8;   // GPUs of one NVSwitch domain
+
 struct SpmmArgs {
     const int64_t *rowptr;
     const int32_t *col;
@@ -55,6 +57,13 @@ struct SpmmArgs {
     int64_t n_hub_chunks;
     int64_t M;
     int dq;  // d / 4
+    // Peer scatter (multi-GPU item partials, chaorec_spmm_csr_push_f32): row r is not stored to y but into the
+    // slot buffer of the GPU that owns it, peer_y[r / peer_block] + ((peer_slot * peer_block + r % peer_block) * d),
+    // a plain store over NVLink issued by the epilogue of the row (or of the hub-finish step).  n_peers == 0: off.
+    float4 *peer_y[kMaxPeers];
+    int n_peers;
+    int peer_slot;
+    int64_t peer_block;
 };
 
 template <int LANES>
@@ -171,6 +180,10 @@ __device__ __forceinline__ void row_epilogue(const SpmmArgs &a, int64_t r, int g
         }
         const int64_t o = r * a.dq + q;
         if (a.y) a.y[o] = yv;                            // next layer gathers these rows: normal policy
+        if (a.n_peers > 0) {
+            const int64_t owner = r / a.peer_block;
+            a.peer_y[owner][(static_cast<int64_t>(a.peer_slot) * a.peer_block + (r - owner * a.peer_block)) * a.dq + q] = yv;
+        }
         if (a.acc) {
             float4 base;
             if (a.acc_mode == 1) {
@@ -210,100 +223,6 @@ __device__ __forceinline__ void rows_body(const SpmmArgs &a, int64_t block) {
 template <int LANES, int NV, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) spmm_rows_kernel(const SpmmArgs a) {
     rows_body<LANES, NV, TPB>(a, blockIdx.x);
-}
-
-// ---- hot-column staging -----------------------------------------------------------------------
-// Both the sub-warp kernel and the hub kernels top out near 6 TB/s of L2->SM traffic whether the
-// gathers hit in L2 or go to HBM (profiles/: rows kernel 45 GB in 8.5 ms, hub chunks 17 GB from
-// DRAM in 2.75 ms), so the lever left is to take traffic OFF the L2->SM path.  Item popularity is
-// Zipf-like: at the 100M-edge config the 768 most frequent columns receive 48 % of all user->item
-// edges.  A persistent CTA stages the x rows of those columns (768 x 256 B = 192 KB) in shared
-// memory once per launch; the CSR carries a second column array in which hot columns are encoded
-// as -1-slot, so the inner loop picks shared or global memory with one sign test.
-struct HotArgs {
-    const int32_t *col_enc;    // [nnz] column index, or -1-slot for a staged column
-    const int32_t *hot_cols;   // [n_hot] slot -> column
-    int n_hot;
-};
-
-template <int LANES, int NV>
-__global__ void __launch_bounds__(1024, 1) spmm_rows_hot_kernel(const SpmmArgs a, const HotArgs h) {
-    extern __shared__ __align__(16) unsigned char hot_smem[];
-    float4 *hot_x = reinterpret_cast<float4 *>(hot_smem);                      // [n_hot][dq]
-    float *hot_cs = reinterpret_cast<float *>(hot_x + static_cast<size_t>(h.n_hot) * a.dq);   // [n_hot]
-    constexpr int kGroups = 1024 / LANES;
-    const int lane = threadIdx.x & 31;
-    const int gl = threadIdx.x % LANES;
-    const int g = threadIdx.x / LANES;
-    const unsigned mask = group_mask<LANES>(lane);
-    for (int sl = g; sl < h.n_hot; sl += kGroups) {
-        const int64_t c = __ldg(h.hot_cols + sl);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            const int q = gl + v * LANES;
-            if (q < a.dq) hot_x[static_cast<size_t>(sl) * a.dq + q] = __ldg(a.x + c * a.dq + q);
-        }
-        if (gl == 0) hot_cs[sl] = a.col_scale ? __ldg(a.col_scale + c) : 1.0f;
-    }
-    __syncthreads();
-    for (int64_t r = static_cast<int64_t>(blockIdx.x) * kGroups + g; r < a.M; r += static_cast<int64_t>(gridDim.x) * kGroups) {
-        const int64_t e_lo = __ldg(a.rowptr + r), e_hi = __ldg(a.rowptr + r + 1);
-        if (a.hub_rows != nullptr && e_hi - e_lo > a.hub_threshold) continue;   // taken by the hub kernels
-        float4 acc[NV];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int64_t e0 = e_lo; e0 < e_hi; e0 += LANES) {
-            const int64_t e = e0 + gl;
-            int c = 0;
-            float w = 0.0f;
-            if (e < e_hi) {
-                c = __ldg(h.col_enc + e);
-                w = a.val ? __ldg(a.val + e) : 1.0f;
-                if (c < 0) w *= hot_cs[-1 - c];
-                else if (a.col_scale) w *= __ldg(a.col_scale + c);
-            }
-            const int cnt = (e_hi - e0 < LANES) ? static_cast<int>(e_hi - e0) : LANES;
-            for (int j = 0; j < cnt; j += 4) {
-                const int nb = (cnt - j < 4) ? (cnt - j) : 4;
-                int cj[4];
-                float wj[4];
-                float4 xv[4][NV];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    cj[t] = __shfl_sync(mask, c, (j + t) % LANES, LANES);
-                    wj[t] = __shfl_sync(mask, w, (j + t) % LANES, LANES);
-                }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if (t < nb) {
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) {
-                            const int q = gl + v * LANES;
-                            if (q < a.dq) {
-                                xv[t][v] = (cj[t] < 0) ? hot_x[static_cast<size_t>(-1 - cj[t]) * a.dq + q]
-                                                       : __ldg(a.x + static_cast<int64_t>(cj[t]) * a.dq + q);
-                            } else {
-                                xv[t][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if (t < nb) {
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) {
-                            acc[v].x = fmaf(wj[t], xv[t][v].x, acc[v].x);
-                            acc[v].y = fmaf(wj[t], xv[t][v].y, acc[v].y);
-                            acc[v].z = fmaf(wj[t], xv[t][v].z, acc[v].z);
-                            acc[v].w = fmaf(wj[t], xv[t][v].w, acc[v].w);
-                        }
-                    }
-                }
-            }
-        }
-        row_epilogue<LANES, NV>(a, r, gl, acc);
-    }
 }
 
 // Sum the partial rows of hub row h in chunk order and apply the row epilogue (one sub-warp).
@@ -421,19 +340,11 @@ __global__ void __launch_bounds__(kThreads) spmm_fused_kernel(const SpmmArgs a) 
 }
 
 template <int LANES, int NV>
-int launch_spmm(const SpmmArgs &a, const HotArgs &h, int64_t n_hub_chunks, cudaStream_t st) {
+int launch_spmm(const SpmmArgs &a, int64_t n_hub_chunks, cudaStream_t st) {
     constexpr int kGroups = kThreads / LANES;
     const int64_t blocks = (a.M + kGroups - 1) / kGroups;
     if (blocks > 0x7fffffffLL) return CHAOREC_E_UNSUPPORTED;
-    if (h.col_enc != nullptr && h.n_hot > 0 && a.M > 0) {
-        const size_t smem = static_cast<size_t>(h.n_hot) * a.dq * 16 + static_cast<size_t>(h.n_hot) * 4 + 16;
-        if (cudaFuncSetAttribute(spmm_rows_hot_kernel<LANES, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem)) != cudaSuccess) {
-            cudaGetLastError();
-            return CHAOREC_E_LAUNCH;
-        }
-        spmm_rows_hot_kernel<LANES, NV><<<sm_count(), 1024, smem, st>>>(a, h);
-    } else if (a.hub_counters != nullptr && a.hub_rows != nullptr && n_hub_chunks > 0) {
+    if (a.hub_counters != nullptr && a.hub_rows != nullptr && n_hub_chunks > 0) {
         if (blocks + n_hub_chunks > 0x7fffffffLL) return CHAOREC_E_UNSUPPORTED;
         spmm_fused_kernel<LANES, NV><<<static_cast<unsigned>(blocks + n_hub_chunks), kThreads, 0, st>>>(a);
         return launch_status();
@@ -544,16 +455,15 @@ extern "C" int chaorec_degree_inv_sqrt(const int64_t *rowptr, int64_t M, float e
     return launch_status();
 }
 
-extern "C" int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *col, const float *val,
-                                        const float *row_scale, const float *col_scale, const float *x, float *y,
-                                        float *acc, float alpha, int32_t acc_mode, const int32_t *hub_rows,
-                                        const int64_t *hub_chunk_ptr, int32_t n_hub, int64_t n_hub_chunks,
-                                        int32_t hub_threshold, int32_t hub_chunk, float *hub_partials,
-                                        int32_t *hub_counters, const int32_t *row_order, const int32_t *hot_col_enc,
-                                        const int32_t *hot_cols, int32_t n_hot, int64_t M, int64_t N, int32_t d,
-                                        void *stream) {
+namespace chaorec {
+namespace {
+int spmm_entry(const int64_t *rowptr, const int32_t *col, const float *val, const float *row_scale, const float *col_scale,
+               const float *x, float *y, float *acc, float alpha, int32_t acc_mode, const int32_t *hub_rows,
+               const int64_t *hub_chunk_ptr, int32_t n_hub, int64_t n_hub_chunks, int32_t hub_threshold, int32_t hub_chunk,
+               float *hub_partials, int32_t *hub_counters, const int32_t *row_order, int64_t M, int64_t N, int32_t d,
+               void *const *peer_y, int32_t n_peers, int64_t peer_block, int32_t peer_slot, void *stream) {
     if (!rowptr || !x || M < 0 || N < 0 || d <= 0) return CHAOREC_E_BADARG;
-    if (!y && !acc) return CHAOREC_E_BADARG;
+    if (!y && !acc && n_peers <= 0) return CHAOREC_E_BADARG;
     if (acc_mode != 0 && acc_mode != 1) return CHAOREC_E_BADARG;
     if (acc && acc_mode == 1 && M != N) return CHAOREC_E_BADARG;
     if (d % 4 != 0 || d > 512) return CHAOREC_E_UNSUPPORTED;
@@ -561,6 +471,9 @@ extern "C" int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *co
     if (hub_rows && n_hub > 0 && (!hub_chunk_ptr || !hub_partials || !aligned16(hub_partials)))
         return CHAOREC_E_BADARG;
     if (hub_threshold < 0 || hub_chunk < 0) return CHAOREC_E_BADARG;
+    if (n_peers < 0 || n_peers > kMaxPeers) return CHAOREC_E_UNSUPPORTED;
+    if (n_peers > 0 && (!peer_y || peer_block <= 0 || peer_slot < 0 || peer_slot >= n_peers || peer_block * n_peers < M))
+        return CHAOREC_E_BADARG;
     if (M == 0) return CHAOREC_OK;
     if (!col) return CHAOREC_E_BADARG;
     SpmmArgs a;
@@ -578,19 +491,57 @@ extern "C" int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *co
     a.hub_threshold = hub_threshold > 0 ? hub_threshold : kHubThreshold;
     a.hub_chunk = hub_chunk > 0 ? hub_chunk : kHubChunk;
     a.M = M; a.dq = d / 4;
+    a.n_peers = n_peers; a.peer_slot = peer_slot; a.peer_block = peer_block > 0 ? peer_block : 1;
+    for (int p = 0; p < kMaxPeers; ++p) {
+        a.peer_y[p] = (p < n_peers) ? reinterpret_cast<float4 *>(peer_y[p]) : nullptr;
+        if (p < n_peers && (!a.peer_y[p] || !aligned16(a.peer_y[p]))) return CHAOREC_E_ALIGN;
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    HotArgs h{};
-    h.col_enc = hot_col_enc; h.hot_cols = hot_cols; h.n_hot = (hot_col_enc && hot_cols) ? n_hot : 0;
-    if (h.n_hot > 0 && static_cast<size_t>(h.n_hot) * d * 4 + static_cast<size_t>(h.n_hot) * 4 + 16 > 220 * 1024)
-        return CHAOREC_E_UNSUPPORTED;
-    if (h.n_hot == 0) h.col_enc = nullptr;
-    if (d == 32) return launch_spmm<8, 1>(a, h, n_hub_chunks, st);
-    if (d == 64) return launch_spmm<16, 1>(a, h, n_hub_chunks, st);
-    if (d <= 128) return launch_spmm<32, 1>(a, h, n_hub_chunks, st);
-    if (d <= 256) return launch_spmm<32, 2>(a, h, n_hub_chunks, st);
-    if (d <= 384) return launch_spmm<32, 3>(a, h, n_hub_chunks, st);
-    return launch_spmm<32, 4>(a, h, n_hub_chunks, st);
+    if (d == 32) return launch_spmm<8, 1>(a, n_hub_chunks, st);
+    if (d == 64) return launch_spmm<16, 1>(a, n_hub_chunks, st);
+    if (d <= 128) return launch_spmm<32, 1>(a, n_hub_chunks, st);
+    if (d <= 256) return launch_spmm<32, 2>(a, n_hub_chunks, st);
+    if (d <= 384) return launch_spmm<32, 3>(a, n_hub_chunks, st);
+    return launch_spmm<32, 4>(a, n_hub_chunks, st);
 }
+
+// Owner side of the fused exchange: rows [0, n_rows) of this GPU's item block.
+//   sum[b] = slots[0][b] + slots[1][b] + ... (rank order: the result does not depend on arrival order)
+//   mode 0: acc_blk[b] += alpha * sum[b];  every peer's table row (block_row0 + b) = sum[b]
+//   mode 1: acc_blk[b] += alpha * sum[b];  every peer's table row (block_row0 + b) = acc_blk[b]   (last layer)
+// One float4 per thread; the G stores of a value go out back to back (G - 1 of them over NVLink).
+struct ReduceBcastArgs {
+    const float4 *slots;
+    float4 *dst[kMaxPeers];
+    float4 *acc_blk;
+    int64_t n_vec;          // n_rows * d / 4
+    int64_t slot_stride;    // peer_block * d / 4
+    int64_t dst_off;        // block_row0 * d / 4
+    int n_peers, mode;
+    float alpha;
+};
+__global__ void __launch_bounds__(256) reduce_slots_bcast_kernel(const ReduceBcastArgs a) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n_vec;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float4 s = __ldcs(a.slots + i);
+        for (int p = 1; p < a.n_peers; ++p) {
+            const float4 v = __ldcs(a.slots + p * a.slot_stride + i);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        float4 out = s;
+        if (a.acc_blk != nullptr) {
+            float4 c = a.acc_blk[i];
+            c.x = fmaf(a.alpha, s.x, c.x); c.y = fmaf(a.alpha, s.y, c.y); c.z = fmaf(a.alpha, s.z, c.z); c.w = fmaf(a.alpha, s.w, c.w);
+            a.acc_blk[i] = c;
+            if (a.mode == 1) out = c;
+        }
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p)
+            if (p < a.n_peers) a.dst[p][a.dst_off + i] = out;
+    }
+}
+}  // namespace
+}  // namespace chaorec
 
 extern "C" int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float *val,
                                     const float *row_scale, const float *col_scale, const float *x, float *y,
@@ -599,9 +550,49 @@ extern "C" int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, c
                                     int32_t hub_threshold, int32_t hub_chunk, float *hub_partials,
                                     int32_t *hub_counters, const int32_t *row_order, int64_t M, int64_t N,
                                     int32_t d, void *stream) {
-    return chaorec_spmm_csr_hot_f32(rowptr, col, val, row_scale, col_scale, x, y, acc, alpha, acc_mode, hub_rows,
-                                    hub_chunk_ptr, n_hub, n_hub_chunks, hub_threshold, hub_chunk, hub_partials,
-                                    hub_counters, row_order, nullptr, nullptr, 0, M, N, d, stream);
+    return spmm_entry(rowptr, col, val, row_scale, col_scale, x, y, acc, alpha, acc_mode, hub_rows, hub_chunk_ptr, n_hub,
+                      n_hub_chunks, hub_threshold, hub_chunk, hub_partials, hub_counters, row_order, M, N, d, nullptr, 0, 0, 0,
+                      stream);
+}
+
+extern "C" int chaorec_spmm_csr_push_f32(const int64_t *rowptr, const int32_t *col, const float *val,
+                                         const float *row_scale, const float *col_scale, const float *x,
+                                         const int32_t *hub_rows, const int64_t *hub_chunk_ptr, int32_t n_hub,
+                                         int64_t n_hub_chunks, int32_t hub_threshold, int32_t hub_chunk,
+                                         float *hub_partials, int32_t *hub_counters, const int32_t *row_order, int64_t M,
+                                         int64_t N, int32_t d, void *const *peer_slots, int32_t n_peers,
+                                         int64_t peer_block, int32_t my_rank, void *stream) {
+    if (n_peers < 1) return CHAOREC_E_BADARG;
+    return spmm_entry(rowptr, col, val, row_scale, col_scale, x, nullptr, nullptr, 0.0f, 0, hub_rows, hub_chunk_ptr, n_hub,
+                      n_hub_chunks, hub_threshold, hub_chunk, hub_partials, hub_counters, row_order, M, N, d, peer_slots, n_peers,
+                      peer_block, my_rank, stream);
+}
+
+extern "C" int chaorec_reduce_slots_broadcast_f32(const float *slots, int32_t n_peers, int64_t peer_block, int64_t n_rows,
+                                                  int32_t d, int64_t block_row0, void *const *peer_tables, float *acc_blk,
+                                                  float alpha, int32_t mode, void *stream) {
+    if (!slots || !peer_tables || n_peers < 1 || n_peers > kMaxPeers || peer_block <= 0 || n_rows < 0 || n_rows > peer_block ||
+        d <= 0 || block_row0 < 0 || (mode != 0 && mode != 1) || (mode == 1 && !acc_blk))
+        return CHAOREC_E_BADARG;
+    if (d % 4 != 0) return CHAOREC_E_UNSUPPORTED;
+    if (!aligned16(slots) || (acc_blk && !aligned16(acc_blk))) return CHAOREC_E_ALIGN;
+    if (n_rows == 0) return CHAOREC_OK;
+    ReduceBcastArgs a{};
+    a.slots = reinterpret_cast<const float4 *>(slots);
+    for (int p = 0; p < kMaxPeers; ++p) {
+        a.dst[p] = (p < n_peers) ? reinterpret_cast<float4 *>(peer_tables[p]) : nullptr;
+        if (p < n_peers && (!a.dst[p] || !aligned16(a.dst[p]))) return CHAOREC_E_ALIGN;
+    }
+    a.acc_blk = reinterpret_cast<float4 *>(acc_blk);
+    a.n_vec = n_rows * (d / 4);
+    a.slot_stride = peer_block * (d / 4);
+    a.dst_off = block_row0 * (d / 4);
+    a.n_peers = n_peers; a.mode = mode; a.alpha = alpha;
+    int64_t blocks = (a.n_vec + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    reduce_slots_bcast_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return launch_status();
 }
 
 extern "C" int chaorec_sddmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float *a, const float *b,

@@ -271,3 +271,104 @@ def propagate_mean_bipartite(shard: BipartiteShard, xu_local: torch.Tensor, xi: 
         acc_i.add_(yi, alpha=alpha)
         xu, xi_cur = yu, yi
     return acc_u, acc_i
+
+
+# ---------------------------------------------------------------------------------------------
+# the same propagation with the item-table exchange FUSED into the kernels (no NCCL call per layer)
+# ---------------------------------------------------------------------------------------------
+
+
+class FusedItemExchange:
+    """Symmetric buffers (every rank holds its peers' addresses: ``torch.distributed._symmetric_memory``, CUDA
+    backend = cuMem IPC handles over NVLink) for the fused exchange of ``propagate_mean_bipartite_fused``:
+
+      ``slots``   [world, block, d]  this rank's inbox: slot s receives rank s's partial rows of MY item block, stored
+                                     by the EPILOGUE of rank s's item-row SpMM (``chaorec_spmm_csr_push_f32``);
+      ``tables``  2 x [world * block, d]  the replicated item table of the current / next layer: every owner sums its
+                                     inbox in rank order and stores the rows into all ranks' tables
+                                     (``chaorec_reduce_slots_broadcast_f32``).
+
+    Per layer and rank: (world-1)/world of the item partials out and the same amount in, both issued by the compute
+    kernels themselves; two device-side barriers (signal pads) order producers and consumers."""
+
+    def __init__(self, num_item: int, d: int, device: torch.device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        rank, world = world_info()
+        if world < 2:
+            raise RuntimeError("FusedItemExchange needs an initialised process group with 2..8 ranks")
+        if world > 8:
+            raise RuntimeError("FusedItemExchange: at most 8 ranks (one NVSwitch domain)")
+        self.rank, self.world, self.d, self.num_item = rank, world, d, num_item
+        self.block = (num_item + world - 1) // world
+        self.n_pad = self.block * world
+        pg = group if group is not None else dist.group.WORLD
+        name = pg.group_name
+        if hasattr(symm, "is_symm_mem_enabled_for_group") and not symm.is_symm_mem_enabled_for_group(name):
+            import warnings
+            with warnings.catch_warnings():      # (a no-op on current torch, required by older releases)
+                warnings.simplefilter("ignore")
+                symm.enable_symm_mem_for_group(name)
+        self.slots = symm.empty((world, self.block, d), dtype=torch.float32, device=device)
+        self.tables = [symm.empty((self.n_pad, d), dtype=torch.float32, device=device) for _ in range(2)]
+        self.h_slots = symm.rendezvous(self.slots, name)
+        self.h_tables = [symm.rendezvous(t, name) for t in self.tables]
+        mk = lambda h: (C.c_void_p * world)(*[int(p) for p in h.buffer_ptrs])
+        self.slot_ptrs = mk(self.h_slots)
+        self.table_ptrs = [mk(h) for h in self.h_tables]
+        self.side = torch.cuda.Stream(device=device)
+        self.slots.zero_()
+        for t in self.tables:
+            t.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+
+    def barrier(self, channel: int) -> None:
+        self.h_slots.barrier(channel=channel)
+
+
+def propagate_mean_bipartite_fused(shard: BipartiteShard, ex: FusedItemExchange, xu_local: torch.Tensor, xi: torch.Tensor,
+                                   n_layers: int, alpha: Optional[float] = None):
+    """``propagate_mean_bipartite`` without a collective call: the item partials leave through the epilogue of the
+    item-row SpMM into their owners' inboxes, the owners reduce (rank order) and store the rows into every rank's
+    item table, and the user-row SpMM of the same layer runs beside both on a second stream.  Same results as the
+    NCCL variant up to the order of the fp32 partial sums (deterministic for a given world size)."""
+    from . import _lib
+    from . import propagate as P
+    lib = _lib.load()
+    rank, world = ex.rank, ex.world
+    dev = xu_local.device
+    d = xu_local.shape[1]
+    I = shard.num_item
+    B = ex.block
+    lo_i = min(rank * B, I)
+    n_rows = max(min((rank + 1) * B, I) - lo_i, 0)
+    if alpha is None:
+        alpha = 1.0 / (n_layers + 1)
+    main = torch.cuda.current_stream(dev)
+    acc_u = xu_local * alpha
+    acc_blk = torch.zeros(B, d, dtype=torch.float32, device=dev)
+    acc_blk[:n_rows] = xi[lo_i:lo_i + n_rows] * alpha
+    xu, xi_cur = xu_local.contiguous(), xi.contiguous()
+    for l in range(n_layers):
+        last = l == n_layers - 1
+        # side stream: user rows of this layer from the (complete) item table of the previous one, fused layer mean
+        ready = main.record_event()
+        ex.side.wait_event(ready)
+        with torch.cuda.stream(ex.side):
+            yu = None if last else torch.empty_like(acc_u)
+            P._spmm_raw(shard.ui, xi_cur, yu, acc_u, alpha, 0)
+            done_u = ex.side.record_event()
+        # main stream: item partials of this layer from the local user rows, stored into the owners' inboxes
+        P._spmm_push(shard.iu, xu, ex.slot_ptrs, world, B, rank)
+        ex.barrier(0)                                   # every rank's partial rows have landed
+        with torch.cuda.device(dev):
+            rc = lib.chaorec_reduce_slots_broadcast_f32(_lib.ptr(ex.slots), world, B, n_rows, d, lo_i, ex.table_ptrs[l % 2],
+                                                        _lib.ptr(acc_blk), float(alpha), 1 if last else 0, _lib.stream_ptr(dev))
+        _lib.check(rc, "chaorec_reduce_slots_broadcast_f32")
+        ex.barrier(1)                                   # every owner's rows have landed in every table
+        main.wait_event(done_u)
+        xu, xi_cur = yu, ex.tables[l % 2][:I]
+    for t in (acc_u, acc_blk):
+        t.record_stream(ex.side)
+    return acc_u, xi_cur

@@ -40,7 +40,6 @@ class CSRGraph:
     row_order: Optional[torch.Tensor] = None      # int32 [M]: rows by decreasing length (large graphs)
     SINGLE_LAUNCH_MAX_NNZ = 1 << 24
     _partials: Dict[int, torch.Tensor] = field(default_factory=dict)
-    _hot: Dict[int, Optional[Tuple[torch.Tensor, torch.Tensor]]] = field(default_factory=dict)
     _transposed: Optional["CSRGraph"] = None
     symmetric: bool = False
 
@@ -105,32 +104,6 @@ class CSRGraph:
             buf = torch.empty(self.n_hub_chunks * d, dtype=torch.float32, device=self.device)
             self._partials[d] = buf
         return buf
-
-    def hot_plan(self, d: int) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
-        """(col_enc int32 [nnz], hot_cols int32 [n_hot]) for the hot-column staging kernel, or None when
-        staging does not pay (small graphs live in L2 anyway; flat column popularity has no hot set)."""
-        if d in self._hot:
-            return self._hot[d]
-        plan = None
-        if os.environ.get("CHAOREC_SPMM_HOT", "0") != "1":
-            # Measured at the 100M-edge config (profiles/README.md): staging the 768 most frequent columns
-            # in shared memory leaves the kernel time unchanged (8.5 ms) -- those rows were L2 hits already
-            # and the kernel is bound by the random HBM gathers of the cold rows.  Kept behind a switch.
-            self._hot[d] = None
-            return None
-        n_hot = min(((200 * 1024) // (4 * d + 4)) // 64 * 64, self.N)
-        if self.nnz >= (1 << 22) and n_hot >= 64:
-            counts = torch.bincount(self.col.to(torch.int64), minlength=self.N)
-            top = torch.topk(counts, n_hot)
-            if float(top.values.sum()) >= 0.10 * self.nnz:
-                hot_cols = top.indices.to(torch.int32).contiguous()
-                slot = torch.full((self.N,), -1, dtype=torch.int32, device=self.device)
-                slot[top.indices] = torch.arange(n_hot, dtype=torch.int32, device=self.device)
-                sc = slot[self.col.to(torch.int64)]
-                col_enc = torch.where(sc >= 0, -1 - sc, self.col).contiguous()
-                plan = (col_enc, hot_cols)
-        self._hot[d] = plan
-        return plan
 
     def transposed(self) -> "CSRGraph":
         """CSR of A^T (for the backward of spmm); symmetric graphs reuse themselves."""
@@ -199,16 +172,26 @@ def _spmm_raw(g: CSRGraph, x: torch.Tensor, y: Optional[torch.Tensor], acc: Opti
               acc_mode: int) -> None:
     lib = _lib.load()
     d = x.shape[1]
-    hot = g.hot_plan(d)
     with torch.cuda.device(x.device):
-        rc = lib.chaorec_spmm_csr_hot_f32(
+        rc = lib.chaorec_spmm_csr_f32(
             _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.val), _lib.ptr(g.row_scale), _lib.ptr(g.col_scale),
             _lib.ptr(x), _lib.ptr(y), _lib.ptr(acc), float(alpha), int(acc_mode), _lib.ptr(g.hub_rows),
             _lib.ptr(g.hub_chunk_ptr), g.n_hub, g.n_hub_chunks, g.hub_threshold, g.hub_chunk, _lib.ptr(g.partials(d)),
-            _lib.ptr(g.hub_counters), _lib.ptr(g.row_order),
-            _lib.ptr(hot[0]) if hot else None, _lib.ptr(hot[1]) if hot else None, int(hot[1].numel()) if hot else 0,
-            g.M, g.N, d, _lib.stream_ptr(x.device))
-    _lib.check(rc, "chaorec_spmm_csr_hot_f32")
+            _lib.ptr(g.hub_counters), _lib.ptr(g.row_order), g.M, g.N, d, _lib.stream_ptr(x.device))
+    _lib.check(rc, "chaorec_spmm_csr_f32")
+
+
+def _spmm_push(g: CSRGraph, x: torch.Tensor, peer_slot_ptrs, n_peers: int, peer_block: int, my_rank: int) -> None:
+    """The product with its rows stored into the owners' slot buffers over NVLink (dist.FusedItemExchange)."""
+    lib = _lib.load()
+    d = x.shape[1]
+    with torch.cuda.device(x.device):
+        rc = lib.chaorec_spmm_csr_push_f32(
+            _lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(g.val), _lib.ptr(g.row_scale), _lib.ptr(g.col_scale),
+            _lib.ptr(x), _lib.ptr(g.hub_rows), _lib.ptr(g.hub_chunk_ptr), g.n_hub, g.n_hub_chunks, g.hub_threshold,
+            g.hub_chunk, _lib.ptr(g.partials(d)), _lib.ptr(g.hub_counters), _lib.ptr(g.row_order), g.M, g.N, d,
+            peer_slot_ptrs, int(n_peers), int(peer_block), int(my_rank), _lib.stream_ptr(x.device))
+    _lib.check(rc, "chaorec_spmm_csr_push_f32")
 
 
 def _check_x(g: CSRGraph, x: torch.Tensor) -> torch.Tensor:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CHAOREC_ABI_VERSION 3   /* 2: hub plan arguments of the SpMM entry points; 3: fallback-row query */
+#define CHAOREC_ABI_VERSION 3   /* 2: hub plan arguments of the SpMM entry points; 3: fallback-row query, fused multi-GPU exchange entry points, hot-column entry removed */
 
 enum {
     CHAOREC_OK = 0,
@@ -107,20 +107,32 @@ int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float 
                          int32_t d, void *stream);
 
 /*
- * Same product with hot-column staging: hot_col_enc int32 [nnz] is `col` with the n_hot most
- * frequent columns replaced by -1-slot, hot_cols int32 [n_hot] maps slot -> column.  The x rows of
- * those columns are staged in shared memory once per launch by persistent CTAs (item popularity
- * is Zipf-like: a few hundred columns receive about half of the user->item gathers), which takes
- * that traffic off the L2->SM path.  n_hot * (4d + 4) must fit in 220 KB.  hot_col_enc == NULL
- * is exactly chaorec_spmm_csr_f32.
+ * Multi-GPU item partials with the exchange fused into the product (one process per GPU, buffers from a symmetric
+ * allocation so that every rank holds its peers' addresses).  Same product as chaorec_spmm_csr_f32, but row r is
+ * not stored locally: the epilogue of the row stores it over NVLink into the slot buffer of the GPU that owns it,
+ *     peer_slots[r / peer_block] + ((my_rank * peer_block + r % peer_block) * d)        (float, [n_peers][peer_block][d])
+ * so the reduce-scatter half of the all-reduce of Model/FREEDOM.py:171-178's item table travels while the product
+ * runs.  peer_slots is a HOST array of n_peers (<= 8) device pointers; peer_block * n_peers >= M.
+ * The caller separates producer and consumer with a cross-GPU barrier (e.g. torch symmetric-memory barrier).
  */
-int chaorec_spmm_csr_hot_f32(const int64_t *rowptr, const int32_t *col, const float *val, const float *row_scale,
-                             const float *col_scale, const float *x, float *y, float *acc, float alpha,
-                             int32_t acc_mode, const int32_t *hub_rows, const int64_t *hub_chunk_ptr,
-                             int32_t n_hub, int64_t n_hub_chunks, int32_t hub_threshold, int32_t hub_chunk,
-                             float *hub_partials, int32_t *hub_counters, const int32_t *row_order,
-                             const int32_t *hot_col_enc, const int32_t *hot_cols, int32_t n_hot, int64_t M, int64_t N,
-                             int32_t d, void *stream);
+int chaorec_spmm_csr_push_f32(const int64_t *rowptr, const int32_t *col, const float *val, const float *row_scale,
+                              const float *col_scale, const float *x, const int32_t *hub_rows,
+                              const int64_t *hub_chunk_ptr, int32_t n_hub, int64_t n_hub_chunks, int32_t hub_threshold,
+                              int32_t hub_chunk, float *hub_partials, int32_t *hub_counters, const int32_t *row_order,
+                              int64_t M, int64_t N, int32_t d, void *const *peer_slots, int32_t n_peers,
+                              int64_t peer_block, int32_t my_rank, void *stream);
+
+/*
+ * Owner side of that exchange: for the n_rows (<= peer_block) rows of this GPU's block,
+ *     sum[b] = slots[0][b] + slots[1][b] + ... + slots[n_peers-1][b]          (fixed rank order: deterministic)
+ *     acc_blk[b] += alpha * sum[b]                                             (running layer mean of the block; nullable)
+ *     row (block_row0 + b) of EVERY peer's table = sum[b] (mode 0) or acc_blk[b] (mode 1, after the last layer)
+ * slots: this GPU's [n_peers][peer_block][d] slot buffer; peer_tables: HOST array of n_peers device pointers to the
+ * [>= block_row0 + n_rows, d] tables (n_peers - 1 of them are written over NVLink).
+ */
+int chaorec_reduce_slots_broadcast_f32(const float *slots, int32_t n_peers, int64_t peer_block, int64_t n_rows, int32_t d,
+                                       int64_t block_row0, void *const *peer_tables, float *acc_blk, float alpha,
+                                       int32_t mode, void *stream);
 
 /*
  * SDDMM on a CSR pattern: out[e] = <a[row(e),:], b[col[e],:]> for every stored edge e (fp32, d % 4 == 0,

@@ -225,37 +225,6 @@ def test_spmm_rejects_bad_shapes():
         cb.spmm(adj, torch.zeros(60, 64))
 
 
-def test_hot_column_staging_matches_plain_kernel():
-    """Zipf column popularity: the persistent kernel that stages the most frequent columns' rows in
-    shared memory must give the same product (forced on a small graph; auto-enabled above 4M nnz)."""
-    U, I, d = 6000, 3000, 64
-    tu, ti = ref_ops.synth_interactions(U, I, 80000, 12)
-    n = U + I
-    row = torch.cat((tu, ti + U)).to(dev())
-    col = torch.cat((ti + U, tu)).to(dev())
-    val = torch.rand(row.numel(), generator=torch.Generator().manual_seed(3)).to(dev())
-    g = cb.csr_from_coo(row, col, val, n, n)
-    g.col_scale = (torch.rand(n, generator=torch.Generator().manual_seed(4)) + 0.5).to(dev())
-    x = ref_ops.xavier_embeddings(n, d, 5).to(dev())
-    g._hot[d] = None
-    plain = cb.spmm(g, x)
-    counts = torch.bincount(g.col.to(torch.int64), minlength=n)
-    top = torch.topk(counts, 768)
-    slot = torch.full((n,), -1, dtype=torch.int32, device=dev())
-    slot[top.indices] = torch.arange(768, dtype=torch.int32, device=dev())
-    sc = slot[g.col.to(torch.int64)]
-    g._hot[d] = (torch.where(sc >= 0, -1 - sc, g.col).contiguous(), top.indices.to(torch.int32).contiguous())
-    assert int((g._hot[d][0] < 0).sum()) > g.nnz // 10
-    hot = cb.spmm(g, x)
-    assert torch.equal(hot, plain)          # same edge order, same arithmetic -> bit-identical
-    # d = 32 path (8 lanes per row) and the fused layer-mean epilogue
-    x32 = x[:, :32].contiguous()
-    g._hot[32] = None
-    p32 = cb.propagate_mean(g, x32, 2)
-    g._hot[32] = g._hot[d]
-    assert torch.equal(cb.propagate_mean(g, x32, 2), p32)
-
-
 def test_device_side_adjacency_builders_match_reference_fixture():
     """V1/V2/V3 graphs built on the device reproduce the reference's results."""
     g = load_golden("freedom_small.npz")
