@@ -118,6 +118,24 @@ def parity_fail(what, detail):
     raise ParityError(f"PARITY GATE FAILED ({what}): {detail} -- no bench line is printed for a wrong result")
 
 
+def collective_gate(fn, world, dev, what):
+    """Runs a per-rank gate; a failure on any rank raises on EVERY rank (nobody is left waiting in a collective)."""
+    msg, out = None, None
+    try:
+        out = fn()
+    except ParityError as exc:
+        msg = str(exc)
+    if world > 1:
+        import torch.distributed as dist
+        flag = torch.tensor([1 if msg else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag) and not msg:
+            msg = f"PARITY GATE FAILED ({what}) on another rank"
+    if msg:
+        raise ParityError(msg)
+    return out
+
+
 def gate_eval(job, lo, hi, dev, ue, ie, mask, world, n_users=8192):
     """A seeded sample of this rank's users + EVERY row the tensor engine handed to the exact engine, re-derived by the
     oracle (oracle/canon.c: canonical fmaf chain, mask value, lowest-index tie-break): ids and score bits must be equal;
@@ -353,7 +371,8 @@ def run_eval_leg(args, dev, rank, world, peaks):
     hits = torch.empty(n_local, dtype=torch.int64, device=dev)
     l2buf = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
-    parity, st = gate_eval(job, lo, hi, dev, ue, ie, mask, world)   # aborts on any mismatch; also: engine, fallback rows
+    # (aborts on any mismatch -- on EVERY rank together, so that no rank is left waiting in a collective)
+    parity, st = collective_gate(lambda: gate_eval(job, lo, hi, dev, ue, ie, mask, world), world, dev, "eval")   # also: engine, fallback rows
 
     def one_step(timed):
         flush_l2(l2buf)
@@ -618,33 +637,49 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
     x0 = torch.randn(n, d, device=dev, generator=gen) * 0.1
     xu0 = x0[shard.u_lo:shard.u_hi].contiguous()
     xi0 = x0[U:].contiguous()
-    # ---- parity gate: this rank's user rows and ALL item rows against the single-GPU product of the same graph
+    # ---- parity gates at N > 1 are COLLECTIVE: every rank measures its own rows against the single-GPU product of the
+    # same graph, the worst error is all-reduced, and all ranks take the same decision.  The headline variant must pass
+    # (else no bench line); a secondary variant that fails is reported as failed and gets no number.
     full_graph, _ = build_full_graph(tu, ti, U, I, dev)
     ref = cb.propagate_mean(full_graph, x0, L)
-    acc_u, acc_i = cdist.propagate_mean_bipartite(shard, xu0, xi0, L)
-    err_b = max(gate_propagate(acc_u, ref[shard.u_lo:shard.u_hi].double(), f"sharded propagate (bipartite, rank {rank})"),
-                gate_propagate(acc_i, ref[U:].double(), f"sharded propagate (bipartite item rows, rank {rank})"))
-    del acc_u, acc_i, x0
-    t_nccl = timed(lambda: cdist.propagate_mean_bipartite(shard, xu0, xi0, L))
-    # ---- the same propagation with the exchange fused into the kernels (peer stores from the SpMM epilogue, owner-side
-    # reduce + store into every table, device-side barriers): gated like the NCCL form, and the headline when available
-    err_f, t = None, t_nccl
-    fused_note = None
+    ref_scale = float(ref.abs().max())
+
+    def shard_err(pairs):
+        e = max(float((got.double() - want.double()).abs().max()) / ref_scale for got, want in pairs)
+        t_ = torch.tensor([e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_[0])
+
+    def nccl_variant():
+        au, ai = cdist.propagate_mean_bipartite(shard, xu0, xi0, L)
+        return shard_err([(au, ref[shard.u_lo:shard.u_hi]), (ai, ref[U:])])
+
+    # ---- headline: the exchange fused into the kernels (peer stores from the SpMM epilogue, owner-side reduce + store
+    # into every table, device-side barriers); falls back to the NCCL form where symmetric memory is unavailable
+    err_f, t_fused, fused_note = None, None, None
     try:
         ex = cdist.FusedItemExchange(I, d, dev)
-        fu, fi = cdist.propagate_mean_bipartite_fused(shard, ex, xu0, xi0, L)
-        err_f = max(gate_propagate(fu, ref[shard.u_lo:shard.u_hi].double(), f"sharded propagate (fused exchange, rank {rank})"),
-                    gate_propagate(fi, ref[U:].double(), f"sharded propagate (fused exchange item rows, rank {rank})"))
-        del fu, fi
-        t_fused = timed(lambda: cdist.propagate_mean_bipartite_fused(shard, ex, xu0, xi0, L))
-        t = t_fused
-        del ex
-    except ParityError:
-        raise
     except Exception as exc:
-        fused_note = f"fused exchange unavailable: {type(exc).__name__}: {exc}"[:300]
-        t_fused = None
-    del ref, shard, xu0, xi0
+        ex, fused_note = None, f"fused exchange unavailable: {type(exc).__name__}: {exc}"[:300]
+    if ex is not None:
+        fu, fi = cdist.propagate_mean_bipartite_fused(shard, ex, xu0, xi0, L)
+        err_f = shard_err([(fu, ref[shard.u_lo:shard.u_hi]), (fi, ref[U:])])
+        del fu, fi
+        if not err_f <= 1e-5:
+            parity_fail("sharded propagate (fused exchange)", f"max|delta|/max|ref| over all ranks = {err_f:.3e} > 1e-5")
+        t_fused = timed(lambda: cdist.propagate_mean_bipartite_fused(shard, ex, xu0, xi0, L))
+    # ---- NCCL all-reduce form of the same sharding
+    err_b = nccl_variant()
+    nccl_note = None
+    if not err_b <= 1e-5:
+        retry = nccl_variant()
+        nccl_note = f"gate failed ({err_b:.3e}); second attempt {retry:.3e}"
+        if ex is None and not retry <= 1e-5:
+            parity_fail("sharded propagate (bipartite, NCCL)", nccl_note)
+        err_b = max(err_b, retry)
+    t_nccl = timed(lambda: cdist.propagate_mean_bipartite(shard, xu0, xi0, L)) if err_b <= 1e-5 else None
+    t = t_fused if t_fused is not None else t_nccl
+    del ref, shard, xu0, xi0, x0, ex
     torch.cuda.empty_cache()
     # --- generic row-cyclic partition, one all-gather of the whole table per layer ------------------
     part = cdist.CyclicPartition(n, world)
@@ -665,15 +700,14 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
     # ---- parity gate: this rank's block against the single-GPU product (node order -> permuted order)
     ref = part.permute_rows(cb.propagate_mean(full_graph, part.unpermute_rows(x0).contiguous(), L))
     blk = cdist.propagate_mean_sharded(graph, part, x0, L)
-    err_c = gate_propagate(blk, ref[rank * part.block:(rank + 1) * part.block].double(), f"sharded propagate (row-cyclic, rank {rank})")
+    ref_scale = float(ref.abs().max())
+    err_c = shard_err([(blk, ref[rank * part.block:(rank + 1) * part.block])])
     del ref, blk, full_graph
-    errs = torch.tensor([err_b, err_c, err_f if err_f is not None else -1.0], dtype=torch.float64, device=dev)
-    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
-    parity = dict(bipartite_nccl_rel_err=float(errs[0]), row_cyclic_nccl_rel_err=float(errs[1]),
-                  bipartite_fused_rel_err=(float(errs[2]) if err_f is not None else None), tol=1e-5, rows_checked="every rank: all rows of its shard",
+    parity = dict(bipartite_fused_rel_err=err_f, bipartite_nccl_rel_err=err_b, bipartite_nccl_note=nccl_note, row_cyclic_nccl_rel_err=err_c,
+                  tol=1e-5, rows_checked="every rank: all rows of its shard; worst error over ranks",
                   reference="single-GPU propagate_mean of the same graph (itself gated against the fp64 chain at N=1)")
     torch.cuda.empty_cache()
-    t_cyclic = timed(lambda: cdist.propagate_mean_sharded(graph, part, x0, L))
+    t_cyclic = timed(lambda: cdist.propagate_mean_sharded(graph, part, x0, L)) if err_c <= 1e-5 else None
     nnz = 2 * E
     bytes_layer = nnz * (4 + 4 * d) + n * (4 * d + 8)
     achieved = bytes_layer * L / t / 1e9 / world
@@ -681,8 +715,8 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
                 exchange=("fused: SpMM epilogue stores item partials into the owners' inboxes over NVLink, owners reduce and store into every "
                           "rank's table (no NCCL call per layer)" if t_fused is not None else "NCCL all-reduce of the item partials"),
                 fused_note=fused_note,
-                bipartite_nccl_allreduce=dict(value=nnz * L / t_nccl, unit="edges/s", ms_per_step=t_nccl * 1e3),
-                generic_row_cyclic_allgather=dict(value=nnz * L / t_cyclic, unit="edges/s", ms_per_step=t_cyclic * 1e3),
+                bipartite_nccl_allreduce=(dict(value=nnz * L / t_nccl, unit="edges/s", ms_per_step=t_nccl * 1e3) if t_nccl else "no number: parity gate failed"),
+                generic_row_cyclic_allgather=(dict(value=nnz * L / t_cyclic, unit="edges/s", ms_per_step=t_cyclic * 1e3) if t_cyclic else "no number: parity gate failed"),
                 config=dict(workload="3-layer propagation, users sharded and kept local, item partials [I, d] exchanged once per layer",
                             users=U, items=I, edges=E, nnz_sym=nnz, d=d, layers=L, world=world, scale=args.scale,
                             exchanged_bytes_per_layer=I * d * 4),
@@ -705,7 +739,7 @@ def run_knn_leg(args, dev, rank, world, peaks):
             x = torch.relu(x)
         kst = {}
         val, idx = cb.knn_topk(x, cfg["k"], row_range=(lo, hi), stats=kst)
-        parity = gate_knn(x, cfg["k"], lo, hi, val, idx)           # aborts on any mismatch
+        parity = collective_gate(lambda: gate_knn(x, cfg["k"], lo, hi, val, idx), world, dev, "knn")   # aborts on any mismatch
         for _ in range(max(1, args.warmup - 1)):
             cb.knn_topk(x, cfg["k"], row_range=(lo, hi))
         torch.cuda.synchronize()

@@ -168,7 +168,7 @@ __device__ __forceinline__ void gather_edges(const SpmmArgs &a, int64_t e_lo, in
 
 // y = row_scale * acc; optional store; optional layer-mean update.
 template <int LANES, int NV>
-__device__ __forceinline__ void row_epilogue(const SpmmArgs &a, int64_t r, int gl, float4 (&acc)[NV]) {
+__device__ __forceinline__ void row_epilogue(const SpmmArgs &a, int64_t r, int gl, float4 (&acc)[NV], bool nonempty = true) {
     const float rs = a.row_scale ? __ldg(a.row_scale + r) : 1.0f;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -180,9 +180,10 @@ __device__ __forceinline__ void row_epilogue(const SpmmArgs &a, int64_t r, int g
         }
         const int64_t o = r * a.dq + q;
         if (a.y) a.y[o] = yv;                            // next layer gathers these rows: normal policy
-        if (a.n_peers > 0) {
-            const int64_t owner = r / a.peer_block;
-            a.peer_y[owner][(static_cast<int64_t>(a.peer_slot) * a.peer_block + (r - owner * a.peer_block)) * a.dq + q] = yv;
+        if (a.n_peers > 0 && nonempty) {                 // (a row without edges is not sent: the owner's inbox is zero there)
+            const uint32_t owner = static_cast<uint32_t>(r) / static_cast<uint32_t>(a.peer_block);   // M < 2^31 in push mode
+            const uint32_t b = static_cast<uint32_t>(r) - owner * static_cast<uint32_t>(a.peer_block);
+            a.peer_y[owner][(static_cast<int64_t>(a.peer_slot) * a.peer_block + b) * a.dq + q] = yv;
         }
         if (a.acc) {
             float4 base;
@@ -216,7 +217,7 @@ __device__ __forceinline__ void rows_body(const SpmmArgs &a, int64_t block) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     gather_edges<LANES, NV, WIDE>(a, e_lo, e_hi, gl, mask, acc);
-    row_epilogue<LANES, NV>(a, r, gl, acc);
+    row_epilogue<LANES, NV>(a, r, gl, acc, e_hi > e_lo);
 }
 
 // CTA size and register cap (minimum resident CTAs) are parameters: see launch_spmm.
@@ -474,6 +475,7 @@ int spmm_entry(const int64_t *rowptr, const int32_t *col, const float *val, cons
     if (n_peers < 0 || n_peers > kMaxPeers) return CHAOREC_E_UNSUPPORTED;
     if (n_peers > 0 && (!peer_y || peer_block <= 0 || peer_slot < 0 || peer_slot >= n_peers || peer_block * n_peers < M))
         return CHAOREC_E_BADARG;
+    if (n_peers > 0 && (M > 0x7fffffffLL || peer_block > 0x7fffffffLL)) return CHAOREC_E_UNSUPPORTED;
     if (M == 0) return CHAOREC_OK;
     if (!col) return CHAOREC_E_BADARG;
     SpmmArgs a;
@@ -511,7 +513,7 @@ int spmm_entry(const int64_t *rowptr, const int32_t *col, const float *val, cons
 //   mode 1: acc_blk[b] += alpha * sum[b];  every peer's table row (block_row0 + b) = acc_blk[b]   (last layer)
 // One float4 per thread; the G stores of a value go out back to back (G - 1 of them over NVLink).
 struct ReduceBcastArgs {
-    const float4 *slots;
+    float4 *slots;
     float4 *dst[kMaxPeers];
     float4 *acc_blk;
     int64_t n_vec;          // n_rows * d / 4
@@ -521,23 +523,32 @@ struct ReduceBcastArgs {
     float alpha;
 };
 __global__ void __launch_bounds__(256) reduce_slots_bcast_kernel(const ReduceBcastArgs a) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n_vec;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        float4 s = __ldcs(a.slots + i);
-        for (int p = 1; p < a.n_peers; ++p) {
-            const float4 v = __ldcs(a.slots + p * a.slot_stride + i);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
+        // all loads of the element first (independent, in flight together), then the sum in rank order, then the stores
+        float4 v[kMaxPeers];
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p)
+            if (p < a.n_peers) v[p] = __ldcs(a.slots + p * a.slot_stride + i);
+        float4 c = zero;
+        if (a.acc_blk != nullptr) c = a.acc_blk[i];
+        float4 s = v[0];
+#pragma unroll
+        for (int p = 1; p < kMaxPeers; ++p)
+            if (p < a.n_peers) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
         float4 out = s;
         if (a.acc_blk != nullptr) {
-            float4 c = a.acc_blk[i];
             c.x = fmaf(a.alpha, s.x, c.x); c.y = fmaf(a.alpha, s.y, c.y); c.z = fmaf(a.alpha, s.z, c.z); c.w = fmaf(a.alpha, s.w, c.w);
             a.acc_blk[i] = c;
             if (a.mode == 1) out = c;
         }
 #pragma unroll
         for (int p = 0; p < kMaxPeers; ++p)
-            if (p < a.n_peers) a.dst[p][a.dst_off + i] = out;
+            if (p < a.n_peers) {
+                a.dst[p][a.dst_off + i] = out;
+                __stcs(a.slots + p * a.slot_stride + i, zero);   // the inbox is zero again for the next layer's (sparse) pushes
+            }
     }
 }
 }  // namespace
@@ -568,7 +579,7 @@ extern "C" int chaorec_spmm_csr_push_f32(const int64_t *rowptr, const int32_t *c
                       peer_block, my_rank, stream);
 }
 
-extern "C" int chaorec_reduce_slots_broadcast_f32(const float *slots, int32_t n_peers, int64_t peer_block, int64_t n_rows,
+extern "C" int chaorec_reduce_slots_broadcast_f32(float *slots, int32_t n_peers, int64_t peer_block, int64_t n_rows,
                                                   int32_t d, int64_t block_row0, void *const *peer_tables, float *acc_blk,
                                                   float alpha, int32_t mode, void *stream) {
     if (!slots || !peer_tables || n_peers < 1 || n_peers > kMaxPeers || peer_block <= 0 || n_rows < 0 || n_rows > peer_block ||
@@ -578,7 +589,7 @@ extern "C" int chaorec_reduce_slots_broadcast_f32(const float *slots, int32_t n_
     if (!aligned16(slots) || (acc_blk && !aligned16(acc_blk))) return CHAOREC_E_ALIGN;
     if (n_rows == 0) return CHAOREC_OK;
     ReduceBcastArgs a{};
-    a.slots = reinterpret_cast<const float4 *>(slots);
+    a.slots = reinterpret_cast<float4 *>(slots);
     for (int p = 0; p < kMaxPeers; ++p) {
         a.dst[p] = (p < n_peers) ? reinterpret_cast<float4 *>(peer_tables[p]) : nullptr;
         if (p < n_peers && (!a.dst[p] || !aligned16(a.dst[p]))) return CHAOREC_E_ALIGN;
@@ -589,7 +600,7 @@ extern "C" int chaorec_reduce_slots_broadcast_f32(const float *slots, int32_t n_
     a.dst_off = block_row0 * (d / 4);
     a.n_peers = n_peers; a.mode = mode; a.alpha = alpha;
     int64_t blocks = (a.n_vec + 255) / 256;
-    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 8;      // one resident wave
     if (blocks > cap) blocks = cap;
     reduce_slots_bcast_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return launch_status();

@@ -278,12 +278,21 @@ def propagate_mean_bipartite(shard: BipartiteShard, xu_local: torch.Tensor, xi: 
 # ---------------------------------------------------------------------------------------------
 
 
+def _mark(stream) -> "torch.cuda.Event":
+    e = torch.cuda.Event(enable_timing=True)
+    e.record(stream)
+    return e
+
+
 class FusedItemExchange:
     """Symmetric buffers (every rank holds its peers' addresses: ``torch.distributed._symmetric_memory``, CUDA
     backend = cuMem IPC handles over NVLink) for the fused exchange of ``propagate_mean_bipartite_fused``:
 
       ``slots``   [world, block, d]  this rank's inbox: slot s receives rank s's partial rows of MY item block, stored
-                                     by the EPILOGUE of rank s's item-row SpMM (``chaorec_spmm_csr_push_f32``);
+                                     by the EPILOGUE of rank s's item-row SpMM (``chaorec_spmm_csr_push_f32``); rows
+                                     without a local edge are not sent at all (the owner re-zeroes its inbox as it
+                                     reads it), which at 8 ranks is close to half of the (item, rank) pairs of a
+                                     Zipf-shaped graph;
       ``tables``  2 x [world * block, d]  the replicated item table of the current / next layer: every owner sums its
                                      inbox in rank order and stores the rows into all ranks' tables
                                      (``chaorec_reduce_slots_broadcast_f32``).
@@ -309,30 +318,38 @@ class FusedItemExchange:
             with warnings.catch_warnings():      # (a no-op on current torch, required by older releases)
                 warnings.simplefilter("ignore")
                 symm.enable_symm_mem_for_group(name)
-        self.slots = symm.empty((world, self.block, d), dtype=torch.float32, device=device)
+        # two inboxes: layer l+1's partial rows may arrive while the owner still reduces layer l's
+        self.slots = [symm.empty((world, self.block, d), dtype=torch.float32, device=device) for _ in range(2)]
         self.tables = [symm.empty((self.n_pad, d), dtype=torch.float32, device=device) for _ in range(2)]
-        self.h_slots = symm.rendezvous(self.slots, name)
+        self.h_slots = [symm.rendezvous(t, name) for t in self.slots]
         self.h_tables = [symm.rendezvous(t, name) for t in self.tables]
         mk = lambda h: (C.c_void_p * world)(*[int(p) for p in h.buffer_ptrs])
-        self.slot_ptrs = mk(self.h_slots)
+        self.slot_ptrs = [mk(h) for h in self.h_slots]
         self.table_ptrs = [mk(h) for h in self.h_tables]
-        self.side = torch.cuda.Stream(device=device)
-        self.slots.zero_()
-        for t in self.tables:
+        # Priorities matter: a one-CTA barrier kernel queued behind a 500k-CTA SpMM of an equal-priority stream waits for
+        # that grid to drain (measured: 1.2 ms per layer on 4 GPUs), so the exchange chain outranks the products.
+        self.side = torch.cuda.Stream(device=device, priority=0)       # user-row SpMM
+        self.push = torch.cuda.Stream(device=device, priority=-1)      # item-row SpMM (push) + barrier 0
+        self.reduce = torch.cuda.Stream(device=device, priority=-2)    # owner-side reduce + broadcast + barrier 1
+        for t in self.slots + self.tables:
             t.zero_()
         torch.cuda.synchronize(device)
         dist.barrier(group=group)
 
     def barrier(self, channel: int) -> None:
-        self.h_slots.barrier(channel=channel)
+        """Device-side barrier of all ranks on the CURRENT stream (signal pads of the first inbox; one channel per
+        stream that may be inside a barrier at the same time)."""
+        self.h_slots[0].barrier(channel=channel)
 
 
 def propagate_mean_bipartite_fused(shard: BipartiteShard, ex: FusedItemExchange, xu_local: torch.Tensor, xi: torch.Tensor,
-                                   n_layers: int, alpha: Optional[float] = None):
+                                   n_layers: int, alpha: Optional[float] = None, timing: Optional[list] = None):
     """``propagate_mean_bipartite`` without a collective call: the item partials leave through the epilogue of the
     item-row SpMM into their owners' inboxes, the owners reduce (rank order) and store the rows into every rank's
-    item table, and the user-row SpMM of the same layer runs beside both on a second stream.  Same results as the
-    NCCL variant up to the order of the fp32 partial sums (deterministic for a given world size)."""
+    item table.  Three streams: the caller's stream runs the item-row products (push), ``ex.reduce`` the owner-side
+    reduce + broadcast, ``ex.side`` the user-row products -- layer l+1's push only needs layer l's user rows, so it
+    runs beside layer l's reduce + broadcast (two inboxes).  Same results as the NCCL variant up to the order of the
+    fp32 partial sums (deterministic for a given world size)."""
     from . import _lib
     from . import propagate as P
     lib = _lib.load()
@@ -345,30 +362,69 @@ def propagate_mean_bipartite_fused(shard: BipartiteShard, ex: FusedItemExchange,
     n_rows = max(min((rank + 1) * B, I) - lo_i, 0)
     if alpha is None:
         alpha = 1.0 / (n_layers + 1)
-    main = torch.cuda.current_stream(dev)
+    caller = torch.cuda.current_stream(dev)
     acc_u = xu_local * alpha
     acc_blk = torch.zeros(B, d, dtype=torch.float32, device=dev)
     acc_blk[:n_rows] = xi[lo_i:lo_i + n_rows] * alpha
     xu, xi_cur = xu_local.contiguous(), xi.contiguous()
+    start = _mark(caller)
+    main = ex.push
+    for st in (ex.side, ex.push, ex.reduce):
+        st.wait_event(start)
+    table_ready = start            # event after which xi_cur is complete on this rank
+    reduced = [None, None]         # per inbox: event after which the owner has consumed (and re-zeroed) it
+    keep = []
     for l in range(n_layers):
         last = l == n_layers - 1
+        k = l % 2
         # side stream: user rows of this layer from the (complete) item table of the previous one, fused layer mean
-        ready = main.record_event()
-        ex.side.wait_event(ready)
+        ex.side.wait_event(table_ready)
         with torch.cuda.stream(ex.side):
             yu = None if last else torch.empty_like(acc_u)
             P._spmm_raw(shard.ui, xi_cur, yu, acc_u, alpha, 0)
-            done_u = ex.side.record_event()
-        # main stream: item partials of this layer from the local user rows, stored into the owners' inboxes
-        P._spmm_push(shard.iu, xu, ex.slot_ptrs, world, B, rank)
-        ex.barrier(0)                                   # every rank's partial rows have landed
-        with torch.cuda.device(dev):
-            rc = lib.chaorec_reduce_slots_broadcast_f32(_lib.ptr(ex.slots), world, B, n_rows, d, lo_i, ex.table_ptrs[l % 2],
-                                                        _lib.ptr(acc_blk), float(alpha), 1 if last else 0, _lib.stream_ptr(dev))
-        _lib.check(rc, "chaorec_reduce_slots_broadcast_f32")
-        ex.barrier(1)                                   # every owner's rows have landed in every table
-        main.wait_event(done_u)
-        xu, xi_cur = yu, ex.tables[l % 2][:I]
-    for t in (acc_u, acc_blk):
-        t.record_stream(ex.side)
+            done_u = _mark(ex.side)
+            if yu is not None:
+                keep.append(yu)
+        # push stream: item partials of this layer from the local user rows, stored into the owners' inboxes k
+        with torch.cuda.stream(main):
+            marks = [_mark(main)] if timing is not None else None
+            if reduced[k] is not None:
+                main.wait_event(reduced[k])             # (all ranks passed barrier 1 of layer l-2: inbox k is free everywhere)
+            P._spmm_push(shard.iu, xu, ex.slot_ptrs[k], world, B, rank)
+            if marks is not None:
+                marks.append(_mark(main))
+            ex.barrier(0)                               # every rank's partial rows of this layer have landed
+            pushed = _mark(main)
+            if marks is not None:
+                marks.append(pushed)
+        # reduce stream: sum my inbox in rank order, store the rows into every rank's table k
+        ex.reduce.wait_event(pushed)
+        with torch.cuda.stream(ex.reduce):
+            with torch.cuda.device(dev):
+                rc = lib.chaorec_reduce_slots_broadcast_f32(_lib.ptr(ex.slots[k]), world, B, n_rows, d, lo_i, ex.table_ptrs[k],
+                                                            _lib.ptr(acc_blk), float(alpha), 1 if last else 0,
+                                                            C_stream(ex.reduce))
+            _lib.check(rc, "chaorec_reduce_slots_broadcast_f32")
+            if marks is not None:
+                marks.append(_mark(ex.reduce))
+            ex.barrier(1)                               # every owner's rows have landed in every table
+            table_ready = _mark(ex.reduce)
+            reduced[k] = table_ready
+            if marks is not None:
+                marks.append(table_ready)
+        main.wait_event(done_u)                         # the next push reads this layer's user rows
+        if marks is not None:
+            marks.append(done_u)
+            timing.append(marks)
+        xu, xi_cur = yu, ex.tables[k][:I]
+    caller.wait_event(table_ready)
+    caller.wait_event(done_u)
+    for t in [acc_u, acc_blk, xi_cur] + keep:
+        for st in (ex.side, ex.push, ex.reduce, caller):
+            t.record_stream(st)
     return acc_u, xi_cur
+
+
+def C_stream(stream: "torch.cuda.Stream"):
+    import ctypes as C
+    return C.c_void_p(stream.cuda_stream)

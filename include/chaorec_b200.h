@@ -112,7 +112,8 @@ int chaorec_spmm_csr_f32(const int64_t *rowptr, const int32_t *col, const float 
  * not stored locally: the epilogue of the row stores it over NVLink into the slot buffer of the GPU that owns it,
  *     peer_slots[r / peer_block] + ((my_rank * peer_block + r % peer_block) * d)        (float, [n_peers][peer_block][d])
  * so the reduce-scatter half of the all-reduce of Model/FREEDOM.py:171-178's item table travels while the product
- * runs.  peer_slots is a HOST array of n_peers (<= 8) device pointers; peer_block * n_peers >= M.
+ * runs.  Rows without an edge are NOT sent (the owner keeps its inbox zero: chaorec_reduce_slots_broadcast_f32 writes
+ * zeros back as it reads).  peer_slots is a HOST array of n_peers (<= 8) device pointers; peer_block * n_peers >= M < 2^31.
  * The caller separates producer and consumer with a cross-GPU barrier (e.g. torch symmetric-memory barrier).
  */
 int chaorec_spmm_csr_push_f32(const int64_t *rowptr, const int32_t *col, const float *val, const float *row_scale,
@@ -124,13 +125,14 @@ int chaorec_spmm_csr_push_f32(const int64_t *rowptr, const int32_t *col, const f
 
 /*
  * Owner side of that exchange: for the n_rows (<= peer_block) rows of this GPU's block,
- *     sum[b] = slots[0][b] + slots[1][b] + ... + slots[n_peers-1][b]          (fixed rank order: deterministic)
+ *     sum[b] = slots[0][b] + slots[1][b] + ... + slots[n_peers-1][b]          (fixed rank order: deterministic);
+ *     slots[*][b] = 0                                                          (ready for the next layer's sparse pushes)
  *     acc_blk[b] += alpha * sum[b]                                             (running layer mean of the block; nullable)
  *     row (block_row0 + b) of EVERY peer's table = sum[b] (mode 0) or acc_blk[b] (mode 1, after the last layer)
  * slots: this GPU's [n_peers][peer_block][d] slot buffer; peer_tables: HOST array of n_peers device pointers to the
  * [>= block_row0 + n_rows, d] tables (n_peers - 1 of them are written over NVLink).
  */
-int chaorec_reduce_slots_broadcast_f32(const float *slots, int32_t n_peers, int64_t peer_block, int64_t n_rows, int32_t d,
+int chaorec_reduce_slots_broadcast_f32(float *slots, int32_t n_peers, int64_t peer_block, int64_t n_rows, int32_t d,
                                        int64_t block_row0, void *const *peer_tables, float *acc_blk, float alpha,
                                        int32_t mode, void *stream);
 

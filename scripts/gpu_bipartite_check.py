@@ -51,6 +51,35 @@ for rep in range(3):                       # buffers are reused across calls: re
     torch.cuda.synchronize()
     ef = max(ef, float((fu - want[shard.u_lo:shard.u_hi]).abs().max() / want.abs().max()),
              float((fi - want[U:]).abs().max() / want.abs().max()))
+# phase times of the fused variant at a size where the exchange matters (optional: CHAOREC_CHECK_BIG=1)
+if os.environ.get("CHAOREC_CHECK_BIG"):
+    Ub, Ib, Eb = 8_388_608, 2_097_152, 100_000_000
+    g = torch.Generator(device=dev).manual_seed(3)
+    w = 1.0 / torch.arange(1, Ib + 1, dtype=torch.float64, device=dev)
+    cdf = torch.cumsum(w / w.sum(), 0)
+    perm = torch.randperm(Ib, generator=g, device=dev)
+    bu = torch.randint(0, Ub, (Eb,), generator=g, device=dev)
+    bi = perm[torch.searchsorted(cdf, torch.rand(Eb, generator=g, device=dev, dtype=torch.float64)).clamp_(max=Ib - 1)]
+    keys = torch.unique(bu * Ib + bi)
+    bu, bi = keys // Ib, keys % Ib
+    del keys
+    sh = cdist.build_bipartite_shard(bu, bi, Ub, Ib)
+    exb = cdist.FusedItemExchange(Ib, d, dev)
+    xb = torch.randn(Ub + Ib, d, device=dev, generator=g) * 0.1
+    xu_b, xi_b = xb[sh.u_lo:sh.u_hi].contiguous(), xb[Ub:].contiguous()
+    del xb
+    for rep in range(4):
+        tm = [] if rep == 3 else None
+        torch.cuda.synchronize(); dist.barrier()
+        cdist.propagate_mean_bipartite_fused(sh, exb, xu_b, xi_b, L, timing=tm)
+        torch.cuda.synchronize()
+    if rank == 0:
+        names = ("push SpMM done", "barrier 0 passed", "reduce+broadcast done", "barrier 1 passed", "user rows done")
+        t00 = tm[0][0]
+        for l, marks in enumerate(tm):
+            print(f"  fused layer {l} (ms since start): push starts {t00.elapsed_time(marks[0]):.3f}, " +
+                  ", ".join(f"{n} {t00.elapsed_time(marks[i + 1]):.3f}" for i, n in enumerate(names)))
+    del sh, exb
 err = torch.tensor([max(eu, ei), ec, ef], device=dev)
 dist.all_reduce(err, op=dist.ReduceOp.MAX)
 ok = bool((err < 1e-5).all())
