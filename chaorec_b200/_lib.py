@@ -35,7 +35,7 @@ SIGNATURES = {
                                        _p, _p, _i64, _i64, _i32, _p]),
     "chaorec_spmm_csr_push_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _i64, _i64, _i32,
                                             _p, _i32, _i64, _i32, _p]),
-    "chaorec_reduce_slots_broadcast_f32": (C.c_int, [_p, _i32, _i64, _i64, _i32, _i64, _p, _p, _f32, _i32, _p]),
+    "chaorec_reduce_slots_broadcast_f32": (C.c_int, [_p, _i32, _i64, _i64, _i32, _i64, _p, _p, _f32, _i32, _p, _i64, _i32, _p]),
     "chaorec_sddmm_csr_f32": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _p]),
     "chaorec_sample_negatives": (C.c_int, [_p, _i64, _p, _p, _i64, _i64, C.c_uint64, C.c_uint64, _p, _p]),
     "chaorec_bpr_loss_grad_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _i64, _f32, _p, _p, _p]),

@@ -521,6 +521,9 @@ struct ReduceBcastArgs {
     int64_t dst_off;        // block_row0 * d / 4
     int n_peers, mode;
     float alpha;
+    const unsigned char *need;   // nullable [n_peers][need_stride]: does peer p read item row r at all?
+    int64_t need_stride, row0;
+    int dq, self;
 };
 __global__ void __launch_bounds__(256) reduce_slots_bcast_kernel(const ReduceBcastArgs a) {
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -543,10 +546,14 @@ __global__ void __launch_bounds__(256) reduce_slots_bcast_kernel(const ReduceBca
             a.acc_blk[i] = c;
             if (a.mode == 1) out = c;
         }
+        // Intermediate layers: a peer whose users touch no edge of this item never gathers the row -- it is not sent
+        // (close to half of the (item, rank) pairs of a Zipf-shaped graph on 8 GPUs).  The last layer's rows are the
+        // result and go everywhere.
+        const int64_t r = a.row0 + i / a.dq;
 #pragma unroll
         for (int p = 0; p < kMaxPeers; ++p)
             if (p < a.n_peers) {
-                a.dst[p][a.dst_off + i] = out;
+                if (a.need == nullptr || a.mode == 1 || p == a.self || __ldg(a.need + p * a.need_stride + r) != 0) a.dst[p][a.dst_off + i] = out;
                 __stcs(a.slots + p * a.slot_stride + i, zero);   // the inbox is zero again for the next layer's (sparse) pushes
             }
     }
@@ -581,7 +588,8 @@ extern "C" int chaorec_spmm_csr_push_f32(const int64_t *rowptr, const int32_t *c
 
 extern "C" int chaorec_reduce_slots_broadcast_f32(float *slots, int32_t n_peers, int64_t peer_block, int64_t n_rows,
                                                   int32_t d, int64_t block_row0, void *const *peer_tables, float *acc_blk,
-                                                  float alpha, int32_t mode, void *stream) {
+                                                  float alpha, int32_t mode, const unsigned char *need, int64_t need_stride,
+                                                  int32_t my_rank, void *stream) {
     if (!slots || !peer_tables || n_peers < 1 || n_peers > kMaxPeers || peer_block <= 0 || n_rows < 0 || n_rows > peer_block ||
         d <= 0 || block_row0 < 0 || (mode != 0 && mode != 1) || (mode == 1 && !acc_blk))
         return CHAOREC_E_BADARG;
@@ -599,6 +607,8 @@ extern "C" int chaorec_reduce_slots_broadcast_f32(float *slots, int32_t n_peers,
     a.slot_stride = peer_block * (d / 4);
     a.dst_off = block_row0 * (d / 4);
     a.n_peers = n_peers; a.mode = mode; a.alpha = alpha;
+    a.need = need; a.need_stride = need_stride; a.row0 = block_row0; a.dq = d / 4; a.self = my_rank;
+    if (need && (need_stride < block_row0 + n_rows || my_rank < 0 || my_rank >= n_peers)) return CHAOREC_E_BADARG;
     int64_t blocks = (a.n_vec + 255) / 256;
     const int64_t cap = static_cast<int64_t>(sm_count()) * 8;      // one resident wave
     if (blocks > cap) blocks = cap;

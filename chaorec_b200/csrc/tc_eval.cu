@@ -576,7 +576,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_b, const EvalArgs a) {
                     : "memory");
                 // (zero padding beyond Nb exists in the last column tiles only; those columns score exactly 0 and, if
                 // a row lists them, the re-score kernel drops them like any other invalid column)
-#if CHAOREC_EV_DEBUG >= 2
+#if CHAOREC_EV_DEBUG == 2 || CHAOREC_EV_DEBUG == 3
                 (void)tcol;                                   // accumulator reads, no filter
                 return;
 #endif
@@ -763,7 +763,7 @@ struct RescoreArgs {
 
 constexpr int kRescoreWarps = 4;
 
-__global__ void __launch_bounds__(kRescoreWarps * 32) rescore_lists_kernel(const RescoreArgs a, const int keys_per_warp) {
+__global__ void __launch_bounds__(kRescoreWarps * 32, 12) rescore_lists_kernel(const RescoreArgs a, const int keys_per_warp) {
     extern __shared__ __align__(16) unsigned char rs_smem[];   // [warps][keys_per_warp] keys, [warps][256] histogram, [warps][EV_SEED_TAB] train items, [warps] key counts
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = static_cast<int64_t>(blockIdx.x) * kRescoreWarps + wib;
@@ -855,6 +855,7 @@ __global__ void __launch_bounds__(kRescoreWarps * 32) rescore_lists_kernel(const
         }
         int P = 64;
         while (P < m) P <<= 1;
+        if (P > keys_per_warp) { P = 64; m = 0; }             // (cannot happen: m <= n <= keys_per_warp, a power of two)
         for (int t = m + lane; t < P; t += 32) keys[t] = 0ull;
         __syncwarp();
         warp_sort_desc_fast(keys, P, lane);
@@ -907,8 +908,23 @@ __global__ void __launch_bounds__(kRescoreWarps * 32) rescore_lists_kernel(const
             }
             keys[t] = make_key(acc, col);
         }
+        // Common case: at most 32 candidates whose K-th best exact score beats mask_value -- no train item can enter the
+        // top K, so the 32 exact keys are ranked in registers and nothing is merged.
+        bool fast = false;
+        if (n_cand <= 32 && a.K <= n_cand) {
+            __syncwarp();
+            uint64_t mykey = lane < n_cand ? keys[lane] : 0ull;
+            warp_sort32_desc_regs(mykey, lane);
+            const uint64_t kth32 = __shfl_sync(0xffffffffu, mykey, a.K - 1);
+            fast = nm == 0 || kth32 > make_key(a.mask_value, 0u);       // (every train item's key is <= the key of column 0)
+            if (fast) {
+                __syncwarp();
+                keys[lane] = mykey;
+            }
+        }
+        __syncwarp();
         // the first K train items re-enter with mask_value (Model/LightGCN.py:150-152)
-        for (int t = n_cand + lane; t < P2; t += 32) {
+        for (int t = n_cand + lane; t < P2 && !fast; t += 32) {
             uint64_t key = 0ull;
             if (t < n_cand + nm) {
                 const int32_t mc = mask_s[t - n_cand];
@@ -917,7 +933,7 @@ __global__ void __launch_bounds__(kRescoreWarps * 32) rescore_lists_kernel(const
             keys[t] = key;
         }
         __syncwarp();
-        warp_sort_desc_fast(keys, P2, lane);
+        if (!fast) warp_sort_desc_fast(keys, P2, lane);
         // ---- certification: a valid column outside the candidate set has approximate (scaled) score <= tmain,
         // hence canonical score <= (tmain + eps') * 2^(ea+eb); the exact top-K is final iff its K-th score is
         // strictly above that.  (The power-of-two factors are exact; eps' is rounded up.)
@@ -1186,7 +1202,10 @@ int tc_eval_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
     {
         // keys of a row: a power of two; a row that lists more (far more than any sane threshold produces) goes to
         // the exact engine
-        const int keys_per_warp = 512;
+        // Keys per row.  256 keeps 12 CTAs per SM resident (measured: 4.8 ms against 6.5 ms with 384 or 512 at 1M x 200k);
+        // a row that lists more goes to the exact engine.  Small item tables get their thresholds from a handful of
+        // sample tiles and do produce rows with 300+ keys (431 of 5000 rows at 6000 items): they keep 512.
+        const int keys_per_warp = e.Nb >= 32768 ? 256 : 512;
         const size_t rs_smem = static_cast<size_t>(kRescoreWarps) * (keys_per_warp * 8 + 256 * 4 + EV_SEED_TAB * 4 + 4);
         ce = cudaFuncSetAttribute(rescore_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rs_smem));
         if (ce != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }

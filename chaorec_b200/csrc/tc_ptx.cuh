@@ -162,6 +162,19 @@ __device__ __forceinline__ void warp_sort64_desc_regs(uint64_t &k0, uint64_t &k1
         k1 = keep_max ? (k1 > o1 ? k1 : o1) : (k1 < o1 ? k1 : o1);
     }
 }
+// 32 keys, one per lane
+__device__ __forceinline__ void warp_sort32_desc_regs(uint64_t &k0, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+        const bool desc = (k == 32) ? true : ((lane & k) == 0);
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool lower = (lane & j) == 0;
+            const uint64_t o0 = __shfl_xor_sync(0xffffffffu, k0, j);
+            k0 = (lower == desc) ? (k0 > o0 ? k0 : o0) : (k0 < o0 ? k0 : o0);
+        }
+    }
+}
 // sort P keys in shared memory (descending): through registers when P == 64
 __device__ __forceinline__ void warp_sort_desc_fast(uint64_t *s, int P, int lane) {
     if (P == 64) {

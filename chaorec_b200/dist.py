@@ -309,6 +309,7 @@ class FusedItemExchange:
         if world > 8:
             raise RuntimeError("FusedItemExchange: at most 8 ranks (one NVSwitch domain)")
         self.rank, self.world, self.d, self.num_item = rank, world, d, num_item
+        self._need = {}
         self.block = (num_item + world - 1) // world
         self.n_pad = self.block * world
         pg = group if group is not None else dist.group.WORLD
@@ -336,6 +337,20 @@ class FusedItemExchange:
         torch.cuda.synchronize(device)
         dist.barrier(group=group)
 
+    def need_map(self, shard: "BipartiteShard") -> torch.Tensor:
+        """uint8 [world, num_item]: need[p][i] != 0 iff some user of rank p has an edge to item i (rank p gathers row i
+        in its user-row product).  Built once per shard: one all-gather of 1 byte per item."""
+        key = id(shard)
+        hit = self._need.get(key)
+        if hit is not None and hit[0] is shard:
+            return hit[1]
+        deg = shard.iu.rowptr[1:] - shard.iu.rowptr[:-1]
+        mine = (deg > 0).to(torch.uint8).contiguous()
+        out = torch.empty(self.world, mine.numel(), dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(out, mine)
+        self._need = {key: (shard, out)}
+        return out
+
     def barrier(self, channel: int) -> None:
         """Device-side barrier of all ranks on the CURRENT stream (signal pads of the first inbox; one channel per
         stream that may be inside a barrier at the same time)."""
@@ -362,6 +377,7 @@ def propagate_mean_bipartite_fused(shard: BipartiteShard, ex: FusedItemExchange,
     n_rows = max(min((rank + 1) * B, I) - lo_i, 0)
     if alpha is None:
         alpha = 1.0 / (n_layers + 1)
+    need = ex.need_map(shard)
     caller = torch.cuda.current_stream(dev)
     acc_u = xu_local * alpha
     acc_blk = torch.zeros(B, d, dtype=torch.float32, device=dev)
@@ -403,6 +419,7 @@ def propagate_mean_bipartite_fused(shard: BipartiteShard, ex: FusedItemExchange,
             with torch.cuda.device(dev):
                 rc = lib.chaorec_reduce_slots_broadcast_f32(_lib.ptr(ex.slots[k]), world, B, n_rows, d, lo_i, ex.table_ptrs[k],
                                                             _lib.ptr(acc_blk), float(alpha), 1 if last else 0,
+                                                            _lib.ptr(need), int(need.shape[1]) if need is not None else 0, rank,
                                                             C_stream(ex.reduce))
             _lib.check(rc, "chaorec_reduce_slots_broadcast_f32")
             if marks is not None:

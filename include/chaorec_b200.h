@@ -131,10 +131,14 @@ int chaorec_spmm_csr_push_f32(const int64_t *rowptr, const int32_t *col, const f
  *     row (block_row0 + b) of EVERY peer's table = sum[b] (mode 0) or acc_blk[b] (mode 1, after the last layer)
  * slots: this GPU's [n_peers][peer_block][d] slot buffer; peer_tables: HOST array of n_peers device pointers to the
  * [>= block_row0 + n_rows, d] tables (n_peers - 1 of them are written over NVLink).
+ * need (nullable, uint8 [n_peers][need_stride], need_stride >= block_row0 + n_rows): need[p][r] != 0 iff some user of
+ * rank p has an edge to item r.  In mode 0 a row is stored only into the tables of the peers that need it (and this
+ * rank's own); mode 1 stores every row everywhere.
  */
 int chaorec_reduce_slots_broadcast_f32(float *slots, int32_t n_peers, int64_t peer_block, int64_t n_rows, int32_t d,
                                        int64_t block_row0, void *const *peer_tables, float *acc_blk, float alpha,
-                                       int32_t mode, void *stream);
+                                       int32_t mode, const unsigned char *need, int64_t need_stride, int32_t my_rank,
+                                       void *stream);
 
 /*
  * SDDMM on a CSR pattern: out[e] = <a[row(e),:], b[col[e],:]> for every stored edge e (fp32, d % 4 == 0,

@@ -80,7 +80,7 @@ mine = (C.c_void_p * world)(*[int(h.buffer_ptrs[rank])] * world)
 
 
 def kb(ptrs):
-    _lib.check(lib.chaorec_reduce_slots_broadcast_f32(_lib.ptr(slots), world, B, B, d, rank * B, ptrs, _lib.ptr(acc), 0.25, 0,
+    _lib.check(lib.chaorec_reduce_slots_broadcast_f32(_lib.ptr(slots), world, B, B, d, rank * B, ptrs, _lib.ptr(acc), 0.25, 0, None, 0, rank,
                                                        _lib.stream_ptr(dev)), "kb")
 
 
