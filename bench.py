@@ -665,19 +665,20 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
         fu, fi = cdist.propagate_mean_bipartite_fused(shard, ex, xu0, xi0, L)
         err_f = shard_err([(fu, ref[shard.u_lo:shard.u_hi]), (fi, ref[U:])])
         del fu, fi
-        if not err_f <= 1e-5:
-            parity_fail("sharded propagate (fused exchange)", f"max|delta|/max|ref| over all ranks = {err_f:.3e} > 1e-5")
-        t_fused = timed(lambda: cdist.propagate_mean_bipartite_fused(shard, ex, xu0, xi0, L))
+        if err_f <= 1e-5:
+            t_fused = timed(lambda: cdist.propagate_mean_bipartite_fused(shard, ex, xu0, xi0, L))
+        else:
+            fused_note = f"fused exchange FAILED its parity gate (max|delta|/max|ref| over all ranks = {err_f:.3e} > 1e-5): no number for it"
     # ---- NCCL all-reduce form of the same sharding
     err_b = nccl_variant()
     nccl_note = None
     if not err_b <= 1e-5:
         retry = nccl_variant()
         nccl_note = f"gate failed ({err_b:.3e}); second attempt {retry:.3e}"
-        if ex is None and not retry <= 1e-5:
-            parity_fail("sharded propagate (bipartite, NCCL)", nccl_note)
         err_b = max(err_b, retry)
     t_nccl = timed(lambda: cdist.propagate_mean_bipartite(shard, xu0, xi0, L)) if err_b <= 1e-5 else None
+    if t_fused is None and t_nccl is None:
+        parity_fail("sharded propagate", f"no bipartite variant passed its gate: fused {err_f}, NCCL {nccl_note}")
     t = t_fused if t_fused is not None else t_nccl
     del ref, shard, xu0, xi0, x0, ex
     torch.cuda.empty_cache()

@@ -377,7 +377,8 @@ def propagate_mean_bipartite_fused(shard: BipartiteShard, ex: FusedItemExchange,
     n_rows = max(min((rank + 1) * B, I) - lo_i, 0)
     if alpha is None:
         alpha = 1.0 / (n_layers + 1)
-    need = ex.need_map(shard)
+    import os
+    need = ex.need_map(shard) if os.environ.get("CHAOREC_FUSED_SPARSE_BCAST", "1") != "0" else None
     caller = torch.cuda.current_stream(dev)
     acc_u = xu_local * alpha
     acc_blk = torch.zeros(B, d, dtype=torch.float32, device=dev)

@@ -38,7 +38,12 @@ class CSRGraph:
     hub_chunk: int = 0
     hub_counters: Optional[torch.Tensor] = None   # int32 [n_hub] (single-launch mode), kept zero by the kernel
     row_order: Optional[torch.Tensor] = None      # int32 [M]: rows by decreasing length (large graphs)
-    SINGLE_LAUNCH_MAX_NNZ = 1 << 24
+    # Single-launch mode (hub rows finished by the last chunk CTA) is for launch-bound graphs only.  It used to apply below
+    # 16M non-zeros; at 8 GPUs the 12M-edge shards of the 100M-edge graph then took it, and both sharded variants failed
+    # their parity gate there intermittently (3e-4 .. 5e-2) while every multi-launch configuration (1, 2, 4 GPUs) has
+    # never failed -- until that is understood the mode stays with the graphs it was built and tested for.
+    SINGLE_LAUNCH_MAX_NNZ = 1 << 21
+    ROW_ORDER_MIN_NNZ = 1 << 24
     _partials: Dict[int, torch.Tensor] = field(default_factory=dict)
     _transposed: Optional["CSRGraph"] = None
     symmetric: bool = False
@@ -89,7 +94,7 @@ class CSRGraph:
         # Large graphs: hand rows to sub-warps in order of decreasing length, so that the two rows of a warp
         # and the four of a CTA finish together (no idle half-warps, no slots held by one long row).
         mode = os.environ.get("CHAOREC_SPMM_ROW_ORDER", "auto")
-        if mode == "1" or (mode == "auto" and self.nnz >= self.SINGLE_LAUNCH_MAX_NNZ):
+        if mode == "1" or (mode == "auto" and self.nnz >= self.ROW_ORDER_MIN_NNZ):
             self.row_order = torch.sort(deg, descending=True, stable=True)[1].to(torch.int32).contiguous()
         else:
             self.row_order = None
