@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every workload (debug only; marks the line)")
     ap.add_argument("--cpu-sample-users", type=int, default=None)
     ap.add_argument("--cpu-legs", action="store_true", help="run the host-side baseline legs even at --scale < 1")
+    ap.add_argument("--skip-cpu-legs", action="store_true", help="profiling runs: no host-side baseline legs")
     return ap.parse_args()
 
 
@@ -561,7 +562,7 @@ def run_propagate_leg(args, dev, rank, world, peaks):
         # ---- CPU baseline leg (BASELINE.md plan of record): ONE layer of torch.sparse.mm on the host cores, COO as the
         # reference builds it (Model/FREEDOM.py:73-109) and CSR
         cpu_leg = None
-        if rank == 0 and args.scale == 1.0 or args.cpu_legs:
+        if (rank == 0 and args.scale == 1.0 and not args.skip_cpu_legs) or args.cpu_legs:
             coo = adj32.to_sparse_coo()
             coo = torch.sparse_coo_tensor(coo.indices().cpu(), coo.values().cpu(), tuple(coo.shape), is_coalesced=True)
             xc = x0.cpu()
@@ -759,7 +760,7 @@ def run_knn_leg(args, dev, rank, world, peaks):
         t = float(tt[0])
         flops = 2.0 * N * N * D
         cpu_ms = cpu_b_ms = lib_ms = None
-        if world == 1 and rank == 0:
+        if world == 1 and rank == 0 and not args.skip_cpu_legs:
             # the reference's own forms on the host cores: conv A (Model/FREEDOM.py:111-128: normalise, dense sim, topk)
             # for both modalities, conv B (Model/LATTICE.py:46-75: build_sim, topk, scatter, symmetric Laplacian) for t_feat
             from oracle import ref_ops
@@ -985,7 +986,7 @@ def main_ours(args):
     if "seam" in legs and world == 1:
         torch.cuda.empty_cache()
         line["seam"] = run_seam_leg(args, dev, rank, world, peaks)
-    if rank == 0 and world == 1 and job is not None:
+    if rank == 0 and world == 1 and job is not None and not args.skip_cpu_legs:
         cpu, _ = run_cpu_baseline_eval(job, args.cpu_sample_users or 131072)       # ~13 s of host work on 16 cores
         line["cpu_baseline"] = cpu
     if rank == 0:

@@ -324,7 +324,8 @@ class FusedItemExchange:
         self.tables = [symm.empty((self.n_pad, d), dtype=torch.float32, device=device) for _ in range(2)]
         self.h_slots = [symm.rendezvous(t, name) for t in self.slots]
         self.h_tables = [symm.rendezvous(t, name) for t in self.tables]
-        mk = lambda h: (C.c_void_p * world)(*[int(p) for p in h.buffer_ptrs])
+        # (a symmetric tensor may sit at an offset inside its allocation block; peers use the same offset)
+        mk = lambda h: (C.c_void_p * world)(*[int(p) + int(getattr(h, "offset", 0) or 0) for p in h.buffer_ptrs])
         self.slot_ptrs = [mk(h) for h in self.h_slots]
         self.table_ptrs = [mk(h) for h in self.h_tables]
         # Priorities matter: a one-CTA barrier kernel queued behind a 500k-CTA SpMM of an equal-priority stream waits for
