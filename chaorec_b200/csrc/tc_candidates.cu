@@ -9,18 +9,20 @@
 // north_star, shared by the kNN builders (Model/FREEDOM.py:114-118) and gene_ranklist
 // (Model/LightGCN.py:147-155).
 //
-// Kernel anatomy (one persistent CTA per SM, 320 threads):
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d loads of a [256 x 64] bf16 slab of A and a
-//               [128 x 64] slab of B per pipeline stage (128-byte swizzle, 3-stage mbarrier ring)
-//   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma
-//               (cta_group::1, kind::f16, M=128, N=128, K=16) for the two 128-row halves of the
-//               A slab; accumulators live in TMEM (2 halves x 2 stages x 128 columns = 512 cols);
+// Kernel anatomy (one persistent CTA per SM, 19 warps = 608 threads, warp-specialised; d > 64 -- the d <= 64
+// evaluation shape has its own kernel, tc_eval.cu):
+//   warps 0-15  epilogue: one thread per (row, 64 columns) of the 256-row x 128-column tile; two
+//               tcgen05.ld.32x32b.x32 per tile, the accumulator stage is handed back right after the loads;
+//               maxima of 4-column groups against the row's running threshold, hot groups examined column by
+//               column with predicated appends to a thread-private list in an L2-resident workspace; lists are
+//               compacted by a warp-cooperative rank selection (two 256-bin histogram passes), batched over the
+//               CTA after tiles 2, 8, 32, 128 ... of a unit
+//   warp 16     TMA producer: cp.async.bulk.tensor.2d loads of a [256 x 64] bf16 slab of A and a [128 x 64] slab
+//               of B per pipeline stage (128-byte swizzle, 3 x 48 KB mbarrier ring)
+//   warps 17-18 MMA issuers, one per accumulator stage (warp 17 owns the TMEM allocation): one elected lane issues
+//               tcgen05.mma (cta_group::1, kind::f16, M=128, N=128, K=16) for the two 128-row halves of the A
+//               slab; accumulators live in TMEM (2 halves x 2 stages x 128 columns = 512 columns);
 //               tcgen05.commit releases smem stages and publishes finished accumulators
-//   warps 2-9   epilogue: thread <-> one row of the 256-row tile (TMEM lane), tcgen05.ld
-//               32x32b.x32 chunks, one FSETP per score against the row's running threshold, the
-//               rare survivors are appended to a thread-private candidate list (L2-resident
-//               workspace); when a list fills, the warp sorts it in shared memory, keeps the best
-//               K' and raises the threshold
 // Work unit = (256-row tile of A, column slice of B); units are dealt round-robin to CTAs.
 #include <cuda.h>
 #include <cuda_bf16.h>

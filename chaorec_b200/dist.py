@@ -85,6 +85,22 @@ def allgather_concat(local: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)
 
 
+def knn_topk_sharded(feats: torch.Tensor, k: int, exclude_self: bool = False, group=None, topk_fn=None):
+    """Item-row sharded kNN build: every rank ranks rows [lo, hi) of the similarity against ALL rows
+    (``knn_topk(..., row_range=...)``), then one all-gather of the [N/G, k] values and indices gives every rank the
+    whole [N, k] result -- what ``get_knn_adj_mat`` / ``build_knn_neighbourhood`` consume.  Bit-identical to the
+    single-GPU call for any world size (rows are independent).  ``topk_fn(feats, k, exclude_self, row_range)``
+    defaults to the CUDA kernel; the gloo tests pass a CPU stand-in."""
+    rank, world = world_info()
+    lo, hi = shard_range(feats.shape[0], world, rank)
+    if topk_fn is None:
+        from .knn import knn_topk as topk_fn
+    val, idx = topk_fn(feats, k, exclude_self=exclude_self, row_range=(lo, hi))
+    if world == 1:
+        return val, idx
+    return allgather_concat(val.contiguous(), group), allgather_concat(idx.contiguous(), group)
+
+
 # ---------------------------------------------------------------------------------------------
 # propagation: cyclic row deal + relabelling
 # ---------------------------------------------------------------------------------------------
@@ -324,10 +340,13 @@ class FusedItemExchange:
         self.tables = [symm.empty((self.n_pad, d), dtype=torch.float32, device=device) for _ in range(2)]
         self.h_slots = [symm.rendezvous(t, name) for t in self.slots]
         self.h_tables = [symm.rendezvous(t, name) for t in self.tables]
-        # (a symmetric tensor may sit at an offset inside its allocation block; peers use the same offset)
-        mk = lambda h: (C.c_void_p * world)(*[int(p) + int(getattr(h, "offset", 0) or 0) for p in h.buffer_ptrs])
-        self.slot_ptrs = [mk(h) for h in self.h_slots]
-        self.table_ptrs = [mk(h) for h in self.h_tables]
+        # (a symmetric tensor may sit at an offset inside its allocation block: the distance between the local tensor
+        # and the local block base is the same on every rank)
+        def mk(h, t):
+            off = int(t.data_ptr()) - int(h.buffer_ptrs[rank])
+            return (C.c_void_p * world)(*[int(p) + off for p in h.buffer_ptrs])
+        self.slot_ptrs = [mk(h, t) for h, t in zip(self.h_slots, self.slots)]
+        self.table_ptrs = [mk(h, t) for h, t in zip(self.h_tables, self.tables)]
         # Priorities matter: a one-CTA barrier kernel queued behind a 500k-CTA SpMM of an equal-priority stream waits for
         # that grid to drain (measured: 1.2 ms per layer on 4 GPUs), so the exchange chain outranks the products.
         self.side = torch.cuda.Stream(device=device, priority=0)       # user-row SpMM

@@ -317,10 +317,44 @@ def lattice_case():
         out["g_" + n] = p.grad.numpy()
     np.savez_compressed(os.path.join(HERE, "lattice_small.npz"), **out)
     print("lattice_small.npz", result.shape, float(result.abs().max()))
+def scipy_adjacency_case():
+    """Adjacency builders V4 / V5 run by the UNMODIFIED reference methods (Model/SimGCL.py:64-104 `get_norm_adj_mat`,
+    Model/MGCN.py:164-196 `get_adj_mat`) on a seeded interaction matrix.  The methods only read num_user, num_item,
+    interaction_matrix and device off `self`, so they are called unbound on a namespace (building the whole models needs
+    feature files).  SimGCL's builder calls `dok_matrix._update`, which newer scipy releases removed: a five-line shim
+    restores exactly what it did (a bulk dict update of the (row, col) -> value entries)."""
+    import types
+    import scipy.sparse as sp
+    if not hasattr(sp.dok_matrix, "_update"):
+        def _update(self, data):
+            for (r, c), v in data.items():
+                self[r, c] = v
+        sp.dok_matrix._update = _update
+    from Model.SimGCL import SimGCL
+    from Model.MGCN import MGCN
+    U, I = 300, 120
+    tu, ti = ref_ops.synth_interactions(U, I, 2200, 17)
+    tu, ti = tu.numpy(), ti.numpy()
+    R = sp.coo_matrix((np.ones(tu.size, dtype=np.float32), (tu, ti)), shape=(U, I))
+    ns = types.SimpleNamespace(num_user=U, num_item=I, interaction_matrix=R, device=torch.device("cpu"))
+    v4 = SimGCL.get_norm_adj_mat(ns).coalesce()
+    v5 = sp.coo_matrix(MGCN.get_adj_mat(ns)).astype(np.float32)
+    # the oracle restatements must reproduce both bit for bit
+    o4 = ref_ops.scipy_norm_adj_v4(tu, ti, U, I).coalesce()
+    o5 = ref_ops.scipy_norm_adj_v5(tu, ti, U, I).coalesce()
+    assert torch.equal(o4.indices(), v4.indices()) and torch.equal(o4.values(), v4.values()), "V4 restatement differs"
+    v5t = torch.sparse_coo_tensor(torch.tensor(np.array([v5.row, v5.col]), dtype=torch.long), torch.tensor(v5.data), (U + I, U + I)).coalesce()
+    assert torch.equal(o5.indices(), v5t.indices()) and torch.equal(o5.values(), v5t.values()), "V5 restatement differs"
+    np.savez_compressed(os.path.join(HERE, "adjacency_v4_v5.npz"), num_user=U, num_item=I, train_u=tu, train_i=ti,
+                        v4_index=v4.indices().numpy(), v4_value=v4.values().numpy(),
+                        v5_index=v5t.indices().numpy(), v5_value=v5t.values().numpy())
+    print("adjacency_v4_v5.npz: V4 nnz", v4.values().numel(), "V5 nnz", v5t.values().numel())
 
 
 if __name__ == "__main__":
-    which = _ARGS or ["lightgcn", "train", "freedom", "metrics", "real", "lattice", "cooccurrence"]
+    which = _ARGS or ["lightgcn", "train", "freedom", "metrics", "real", "lattice", "cooccurrence", "scipy_adjacency"]
+    if "scipy_adjacency" in which:
+        scipy_adjacency_case()
     if "lattice" in which:
         lattice_case()
     if "cooccurrence" in which:

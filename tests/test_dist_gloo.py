@@ -108,6 +108,21 @@ def _worker(rank, world, port, results):
         if rank == 0:
             got = torch.cat((all_u, ai))
             results["bip_err"] = float((got - want).abs().max() / want.abs().max())
+
+        # --- kNN build: rows sharded, [N/G, k] outputs all-gathered --------------------------------
+        feats = torch.randn(97, 12, generator=torch.Generator().manual_seed(9))
+
+        def cpu_topk(x, k, exclude_self=False, row_range=None):
+            xn = x / x.norm(dim=1, keepdim=True)
+            lo_, hi_ = row_range
+            sim = xn[lo_:hi_] @ xn.t()
+            v_, i_ = torch.sort(sim, dim=1, descending=True, stable=True)
+            return v_[:, :k].contiguous(), i_[:, :k].contiguous()
+
+        kv, ki = cdist.knn_topk_sharded(feats, 5, topk_fn=cpu_topk)
+        wv, wi = cpu_topk(feats, 5, row_range=(0, 97))
+        if rank == 0:
+            results["knn_ok"] = bool(torch.equal(ki, wi) and torch.allclose(kv, wv, atol=1e-6))   # (per-row-block GEMMs may round differently)
     finally:
         dist.destroy_process_group()
 
@@ -119,6 +134,7 @@ def test_world_size_2_sharding_and_collectives():
     assert results["metrics_ok"] is True
     assert results["prop_err"] < 1e-5
     assert results["bip_err"] < 1e-5
+    assert results["knn_ok"] is True
 
 
 def test_shard_range_covers_everything():

@@ -251,7 +251,19 @@ def test_device_side_adjacency_builders_match_reference_fixture():
     v1 = cb.bipartite_graph(tr[:, 0], tr[:, 1] - U1, U1, I1, "v1")
     x1 = torch.from_numpy(np.concatenate([l["user_w"], l["item_w"]])).to(dev())
     assert rel_err(cb.propagate_mean(v1, x1, int(l["n_layers"])), torch.from_numpy(l["result"])) <= REL
-    # V4 / V5: the scipy builders of SimGCL & co. / MGCN (restated in the oracle; the reference's code needs scipy 1.10)
+    # V4 / V5 against the adjacency the UNMODIFIED reference methods built (tests/golden/adjacency_v4_v5.npz)
+    a = load_golden("adjacency_v4_v5.npz")
+    Ua, Ia = int(a["num_user"]), int(a["num_item"])
+    xa = ref_ops.xavier_embeddings(Ua + Ia, 64, 5)
+    for variant in ("v4", "v5"):
+        ref_adj = torch.sparse_coo_tensor(torch.from_numpy(a[variant + "_index"]), torch.from_numpy(a[variant + "_value"]), (Ua + Ia, Ua + Ia))
+        gv = cb.bipartite_graph(torch.from_numpy(a["train_u"]).to(dev()), torch.from_numpy(a["train_i"]).to(dev()), Ua, Ia, variant)
+        assert rel_err(cb.spmm(gv, xa.to(dev())), torch.sparse.mm(ref_adj, xa)) <= REL
+        # duplicated training pairs collapse to one entry in the scipy dok / lil builders
+        gd = cb.bipartite_graph(torch.from_numpy(np.concatenate((a["train_u"], a["train_u"][:50]))).to(dev()),
+                                torch.from_numpy(np.concatenate((a["train_i"], a["train_i"][:50]))).to(dev()), Ua, Ia, variant)
+        assert torch.equal(cb.spmm(gd, xa.to(dev())), cb.spmm(gv, xa.to(dev())))
+    # ... and against the oracle restatements on the LightGCN fixture graph
     tu4, ti4 = tr[:, 0].cpu(), (tr[:, 1] - U1).cpu()
     for variant, build in (("v4", ref_ops.scipy_norm_adj_v4), ("v5", ref_ops.scipy_norm_adj_v5)):
         gv = cb.bipartite_graph(tr[:, 0], tr[:, 1] - U1, U1, I1, variant)
