@@ -1048,12 +1048,7 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
         p.mask_rowptr = nullptr; p.mask_col = nullptr; p.exclude_self = 0;
         p.kp = k_seed; p.cand_out = nullptr; p.tprime_out = tau0; p.tau0 = nullptr; p.debug_mode = 0;
         const int pgrid = p.n_row_tiles < sm_count() ? p.n_row_tiles : sm_count();
-        if (e.d <= BK) {
-            const size_t smem = tc_smem_bytes<true>();
-            ce = cudaFuncSetAttribute(tc_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            if (ce != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
-            tc_candidates_kernel<true><<<pgrid, kTcThreads, smem, stm>>>(map_a, map_bs, p);
-        } else {
+        {   // (d <= 64 never gets here: tc_eval.cu; the resident-A instantiation of this kernel is no longer built)
             const size_t smem = tc_smem_bytes<false>();
             ce = cudaFuncSetAttribute(tc_candidates_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (ce != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
@@ -1061,12 +1056,7 @@ int tc_topk_launch(const EngineArgs &e, void *workspace, size_t workspace_bytes,
         }
         t.tau0 = tau0; t.tau0_lists = hs.CH;
     }
-    if (e.d <= BK) {
-        const size_t smem = tc_smem_bytes<true>();
-        ce = cudaFuncSetAttribute(tc_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (ce != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
-        tc_candidates_kernel<true><<<grid, kTcThreads, smem, stm>>>(map_a, map_b, t);
-    } else {
+    {
         const size_t smem = tc_smem_bytes<false>();
         ce = cudaFuncSetAttribute(tc_candidates_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (ce != cudaSuccess) { cudaGetLastError(); return CHAOREC_E_LAUNCH; }
