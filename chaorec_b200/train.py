@@ -82,12 +82,14 @@ def sample_negatives(users: torch.Tensor, train_items, num_item: int, seed: int,
 
 
 def training_batches(edge_users: torch.Tensor, edge_pos_items: torch.Tensor, train_items, num_user: int,
-                     num_item: int, batch_size: int, epoch: int, seed: int = 0):
+                     num_item: int, batch_size: int, epoch: int, seed: int = 0, drop_last: bool = False):
     """One epoch of ``DataLoader(TrainingDataset(...), batch_size, shuffle=True)`` (dataload.py:60-106,
     main.py's loader) without leaving the GPU: yields ``(users, pos_items, neg_items)`` int64 device tensors,
     items as GLOBAL ids like the reference's triples.  ``edge_users`` / ``edge_pos_items`` are the training
     pairs (global item ids) on the device.  The permutation comes from a device generator seeded with
-    ``(seed, epoch)``; negatives from :func:`sample_negatives`."""
+    ``(seed, epoch)``; negatives from :func:`sample_negatives`.  ``drop_last=True`` skips a short final batch (what
+    ``GraphedLightGCNStep``, whose captured kernels have the batch size baked in, needs; the reference's DataLoader
+    keeps it)."""
     n = int(edge_users.numel())
     gen = torch.Generator(device=edge_users.device)
     gen.manual_seed((int(seed) * 1000003 + int(epoch)) & 0x7FFFFFFFFFFFFFFF)
@@ -97,6 +99,8 @@ def training_batches(edge_users: torch.Tensor, edge_pos_items: torch.Tensor, tra
     neg_all = sample_negatives(users_all, train_items, num_item, seed, first_draw=int(epoch) * n, item_offset=num_user)
     for lo in range(0, n, batch_size):
         hi = min(lo + batch_size, n)
+        if drop_last and hi - lo < batch_size:
+            break
         yield users_all[lo:hi], pos_all[lo:hi], neg_all[lo:hi]
 
 

@@ -53,7 +53,7 @@ for rep in range(3):                       # buffers are reused across calls: re
              float((fi - want[U:]).abs().max() / want.abs().max()))
 # phase times of the fused variant at a size where the exchange matters (optional: CHAOREC_CHECK_BIG=1)
 if os.environ.get("CHAOREC_CHECK_BIG"):
-    Ub, Ib, Eb = 8_388_608, 2_097_152, 100_000_000
+    Ub, Ib, Eb = 8_388_608, 2_097_152, int(os.environ.get("CHAOREC_CHECK_EDGES", "100000000"))
     g = torch.Generator(device=dev).manual_seed(3)
     w = 1.0 / torch.arange(1, Ib + 1, dtype=torch.float64, device=dev)
     cdf = torch.cumsum(w / w.sum(), 0)
@@ -67,11 +67,16 @@ if os.environ.get("CHAOREC_CHECK_BIG"):
     exb = cdist.FusedItemExchange(Ib, d, dev)
     xb = torch.randn(Ub + Ib, d, device=dev, generator=g) * 0.1
     xu_b, xi_b = xb[sh.u_lo:sh.u_hi].contiguous(), xb[Ub:].contiguous()
+    want_b = None
+    if os.environ.get("CHAOREC_CHECK_BIG_PARITY"):      # the whole graph on every rank: single-GPU reference rows
+        fullb = cb.bipartite_graph(bu, bi, Ub, Ib, "v1")
+        want_b = cb.propagate_mean(fullb, xb, L)
+        del fullb
     del xb
     for rep in range(4):
         tm = [] if rep == 3 else None
         torch.cuda.synchronize(); dist.barrier()
-        cdist.propagate_mean_bipartite_fused(sh, exb, xu_b, xi_b, L, timing=tm)
+        fub, fib = cdist.propagate_mean_bipartite_fused(sh, exb, xu_b, xi_b, L, timing=tm)
         torch.cuda.synchronize()
     if rank == 0:
         names = ("push SpMM done", "barrier 0 passed", "reduce+broadcast done", "barrier 1 passed", "user rows done")
@@ -79,6 +84,15 @@ if os.environ.get("CHAOREC_CHECK_BIG"):
         for l, marks in enumerate(tm):
             print(f"  fused layer {l} (ms since start): push starts {t00.elapsed_time(marks[0]):.3f}, " +
                   ", ".join(f"{n} {t00.elapsed_time(marks[i + 1]):.3f}" for i, n in enumerate(names)))
+    if want_b is not None:
+        sc = float(want_b.abs().max())
+        eb = torch.tensor([float((fub - want_b[sh.u_lo:sh.u_hi]).abs().max()) / sc, float((fib - want_b[Ub:]).abs().max()) / sc], device=dev)
+        allb = [torch.zeros_like(eb) for _ in range(world)]
+        dist.all_gather(allb, eb)
+        if rank == 0:
+            print(f"  fused exchange on the big graph ({int(bu.numel())} edges), per rank (user rows, item rows) rel err: " +
+                  " ".join(f"({float(e[0]):.1e},{float(e[1]):.1e})" for e in allb))
+        ef = max(ef, float(eb.max()))
     del sh, exb
 err = torch.tensor([max(eu, ei), ec, ef], device=dev)
 dist.all_reduce(err, op=dist.ReduceOp.MAX)
