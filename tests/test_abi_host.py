@@ -182,3 +182,22 @@ def test_conversion_caches_are_keyed_by_object_identity_not_by_a_recyclable_id()
     for i in range(20):                                 # bounded
         ranking._cache_put(cache, np.empty(3, dtype=object), fake(i))
     assert len(cache) <= ranking._CACHE_ENTRIES
+
+
+def test_host_side_argument_checks_of_the_round_2_entry_points():
+    """No GPU needed: argument validation of the fused-exchange entry points (C side) and of the python shims."""
+    lib = _lib.load()
+    import ctypes as C
+    one = (C.c_void_p * 1)(0)
+    # push: needs peers, a slot inside [0, n_peers), enough blocks for the rows
+    assert lib.chaorec_spmm_csr_push_f32(None, None, None, None, None, None, None, None, 0, 0, 0, 0, None, None, None, 8, 8, 64,
+                                         one, 0, 4, 0, None) != 0
+    assert lib.chaorec_reduce_slots_broadcast_f32(None, 2, 4, 4, 64, 0, one, None, 0.25, 0, None, 0, 0, None) != 0
+    assert b"bad argument" in lib.chaorec_error_string(-1) or lib.chaorec_error_string(-1) is not None
+    # python shims
+    with pytest.raises(RuntimeError, match="pair up"):
+        cb.rank_topk_sum([torch.zeros(2, 4)], [], None, 1)
+    from chaorec_b200 import dist as cdist
+    with pytest.raises(RuntimeError, match="process group"):
+        cdist.FusedItemExchange(10, 64, torch.device("cpu"))
+    assert cdist.shard_range(10, 8, 7) == (9, 10)
