@@ -184,6 +184,11 @@ __device__ __forceinline__ void row_epilogue(const SpmmArgs &a, int64_t r, int g
             const uint32_t owner = static_cast<uint32_t>(r) / static_cast<uint32_t>(a.peer_block);   // M < 2^31 in push mode
             const uint32_t b = static_cast<uint32_t>(r) - owner * static_cast<uint32_t>(a.peer_block);
             a.peer_y[owner][(static_cast<int64_t>(a.peer_slot) * a.peer_block + b) * a.dq + q] = yv;
+            // The store must have LANDED before this kernel counts as complete: the consumer is released by a flag that
+            // a later kernel writes over NVLink, and nothing orders that flag behind posted stores still in flight
+            // (without row_order every rank writes to the same owner at the same time -- the one configuration whose
+            // gate failed).
+            __threadfence_system();
         }
         if (a.acc) {
             float4 base;
@@ -557,6 +562,7 @@ __global__ void __launch_bounds__(256) reduce_slots_bcast_kernel(const ReduceBca
                 __stcs(a.slots + p * a.slot_stride + i, zero);   // the inbox is zero again for the next layer's (sparse) pushes
             }
     }
+    __threadfence_system();     // (the rows stored into the peers' tables have landed when the kernel completes)
 }
 }  // namespace
 }  // namespace chaorec

@@ -145,3 +145,70 @@ def test_shard_range_covers_everything():
             assert all(bounds[i][1] == bounds[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in bounds]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_fused_exchange_protocol_in_one_process():
+    """The algorithm of dist.propagate_mean_bipartite_fused restated with CPU tensors for G ranks in one process
+    (sparse pushes into per-owner inboxes that the owner re-zeroes, rank-ordered owner-side reduce, rows broadcast
+    only to the ranks that gather them, two inboxes / two tables, last layer broadcasts the layer mean) against the
+    single-process propagation -- the protocol is right for any world size, including 8 on a graph where most
+    (item, rank) pairs have no edge."""
+    for G, U, I, E in ((8, 160, 257, 900), (4, 64, 50, 600), (2, 33, 17, 200)):
+        d, L = 8, 3
+        tu, ti = ref_ops.synth_interactions(U, I, E, 7 + G, min_deg=1)
+        ei = ref_ops.symmetrise_edges(torch.stack((tu, ti + U), 1).numpy())
+        gen = torch.Generator().manual_seed(G)
+        xu0, xi0 = torch.randn(U, d, generator=gen), torch.randn(I, d, generator=gen)
+        want = ref_ops.lightgcn_forward(xu0, xi0, ei, L)
+        alpha = 1.0 / (L + 1)
+        B = (I + G - 1) // G
+        item_deg = torch.bincount(ti, minlength=I).float()
+        ranks = []
+        for r in range(G):
+            u_lo, u_hi = cdist.shard_range(U, G, r)
+            mine = (tu >= u_lo) & (tu < u_hi)
+            lu, li = tu[mine] - u_lo, ti[mine]
+            udeg = torch.bincount(lu, minlength=u_hi - u_lo).float()
+            w = udeg.pow(-0.5)[lu] * item_deg.pow(-0.5)[li]
+            w[torch.isinf(w)] = 0
+            ranks.append(dict(u_lo=u_lo, u_hi=u_hi,
+                              ui=torch.sparse_coo_tensor(torch.stack((lu, li)), w, (u_hi - u_lo, I)),
+                              iu=torch.sparse_coo_tensor(torch.stack((li, lu)), w, (I, u_hi - u_lo)),
+                              has=torch.bincount(li, minlength=I) > 0,
+                              inbox=[torch.zeros(G, B, d), torch.zeros(G, B, d)],
+                              table=[torch.full((G * B, d), float("nan")), torch.full((G * B, d), float("nan"))],
+                              xu=xu0[u_lo:u_hi].clone(), xi=xi0.clone(), acc_u=xu0[u_lo:u_hi] * alpha,
+                              acc_blk=torch.zeros(B, d)))
+        for r, s in enumerate(ranks):
+            lo, hi = min(r * B, I), min((r + 1) * B, I)
+            s["acc_blk"][:hi - lo] = xi0[lo:hi] * alpha
+        for l in range(L):
+            k, last = l % 2, l == L - 1
+            new_xu = []
+            for s in ranks:                                   # user rows from the previous item table (only needed rows are valid)
+                xi = torch.where(s["has"].unsqueeze(1), s["xi"][:I], torch.zeros(()))    # rows it does not gather may hold anything
+                yu = torch.sparse.mm(s["ui"], xi)
+                s["acc_u"] = s["acc_u"] + alpha * yu
+                new_xu.append(yu)
+            for r, s in enumerate(ranks):                     # push: only rows with a local edge leave
+                part = torch.sparse.mm(s["iu"], s["xu"])
+                for i in torch.nonzero(s["has"]).flatten().tolist():
+                    ranks[i // B]["inbox"][k][r, i % B] = part[i]
+            for o, s in enumerate(ranks):                     # owner: rank-ordered sum, re-zero, sparse broadcast
+                lo, hi = min(o * B, I), min((o + 1) * B, I)
+                tot = torch.zeros(B, d)
+                for p in range(G):
+                    tot = tot + s["inbox"][k][p]
+                s["inbox"][k].zero_()
+                s["acc_blk"] = s["acc_blk"] + alpha * tot
+                out = s["acc_blk"] if last else tot
+                for p, t in enumerate(ranks):
+                    for b in range(hi - lo):
+                        if last or p == o or bool(t["has"][lo + b]):
+                            t["table"][k][lo + b] = out[b]
+            for s, yu in zip(ranks, new_xu):
+                s["xu"], s["xi"] = yu, s["table"][k]
+        got_u = torch.cat([s["acc_u"] for s in ranks])
+        for s in ranks:
+            got = torch.cat((got_u, s["table"][(L - 1) % 2][:I]))
+            assert float((got - want).abs().max() / want.abs().max()) < 1e-5, (G, "rank result differs")
