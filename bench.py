@@ -612,9 +612,30 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
     import chaorec_b200 as cb
     from chaorec_b200 import _lib, dist as cdist
     cfg = PROP_CFG
-    U, I, tu, ti = gpu_zipf_graph(cfg, args.scale, dev)          # same seed on every rank -> same graph
+    U, I, tu, ti = gpu_zipf_graph(cfg, args.scale, dev)          # same seed on every rank -> (should be) the same graph
     n, d, L = U + I, cfg["d"], cfg["L"]
-    E = int(tu.numel())
+    # Every rank must work on the SAME graph and the same layer-0 table.  They are generated per rank from the same seeds;
+    # whether that really gave identical tensors is recorded (`inputs_identical_across_ranks`), and rank 0's copies are
+    # broadcast, so that the gates below cannot be tripped by an input that differs between GPUs.
+    chk = torch.stack((torch.tensor(tu.numel(), device=dev), (tu * 31 + ti).sum(), (tu ^ ti).sum())).to(torch.int64)
+    all_chk = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(all_chk, chk)
+    graphs_identical = all(bool(torch.equal(c, all_chk[0])) for c in all_chk)
+    e_n = all_chk[0][0:1].clone()
+    E = int(e_n)
+    if rank != 0 and int(tu.numel()) != E:
+        tu, ti = torch.empty(E, dtype=torch.int64, device=dev), torch.empty(E, dtype=torch.int64, device=dev)
+    tu, ti = tu.contiguous(), ti.contiguous()
+    dist.broadcast(tu, 0)
+    dist.broadcast(ti, 0)
+
+    def same_on_all_ranks(t):
+        """True when the tensor generated on this rank equals rank 0's; the tensor is then replaced by rank 0's copy."""
+        mine = t.clone()
+        dist.broadcast(t, 0)
+        flag = torch.tensor([1 if torch.equal(mine, t) else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(int(flag))
 
     def timed(fn):
         for _ in range(args.warmup):
@@ -636,6 +657,7 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
     shard = cdist.build_bipartite_shard(tu, ti, U, I)
     gen = torch.Generator(device=dev).manual_seed(1)
     x0 = torch.randn(n, d, device=dev, generator=gen) * 0.1
+    x0_identical = same_on_all_ranks(x0)
     xu0 = x0[shard.u_lo:shard.u_hi].clone()      # (copies, not views: .contiguous() of a row slice is the slice itself)
     xi0 = x0[U:].clone()
     # ---- parity gates at N > 1 are COLLECTIVE: every rank measures its own rows against the single-GPU product of the
@@ -720,6 +742,7 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
     graph.row_scale = dis_perm[rank * part.block:(rank + 1) * part.block].contiguous()
     graph.col_scale = dis_perm
     x0 = torch.randn(part.n_padded, d, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 0.1
+    x0_identical = same_on_all_ranks(x0) and x0_identical
     # ---- parity gate: this rank's block against the single-GPU product (node order -> permuted order)
     ref = part.permute_rows(cb.propagate_mean(full_graph, part.unpermute_rows(x0).contiguous(), L))
     blk = cdist.propagate_mean_sharded(graph, part, x0, L)
@@ -728,6 +751,8 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
     del ref, blk, full_graph
     parity = dict(bipartite_fused_rel_err=err_f, bipartite_nccl_rel_err=err_b, bipartite_nccl_note=nccl_note, row_cyclic_nccl_rel_err=err_c,
                   fused_vs_nccl_rel_err=keep_fused.get("agree"),
+                  inputs_identical_across_ranks=dict(graph=graphs_identical, layer0_table=x0_identical,
+                                                     note="generated per rank from the same seeds; rank 0's copies are broadcast and used"),
                   tol=1e-5, rows_checked="every rank: all rows of its shard; worst error over ranks",
                   reference="single-GPU propagate_mean of the same graph (itself gated against the fp64 chain at N=1)")
     torch.cuda.empty_cache()
