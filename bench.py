@@ -741,10 +741,12 @@ def run_propagate_leg_sharded(args, dev, rank, world, peaks):
     dis_perm[torch.isinf(dis_perm)] = 0
     graph.row_scale = dis_perm[rank * part.block:(rank + 1) * part.block].contiguous()
     graph.col_scale = dis_perm
-    x0 = torch.randn(part.n_padded, d, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 0.1
-    x0_identical = same_on_all_ranks(x0) and x0_identical
+    x0_nodes = torch.randn(n, d, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 0.1
+    x0_identical = same_on_all_ranks(x0_nodes) and x0_identical
+    x0 = part.permute_rows(x0_nodes)       # (padding rows of the permuted numbering are zero: they have no edges)
     # ---- parity gate: this rank's block against the single-GPU product (node order -> permuted order)
-    ref = part.permute_rows(cb.propagate_mean(full_graph, part.unpermute_rows(x0).contiguous(), L))
+    ref = part.permute_rows(cb.propagate_mean(full_graph, x0_nodes, L))
+    del x0_nodes
     blk = cdist.propagate_mean_sharded(graph, part, x0, L)
     ref_scale = float(ref.abs().max())
     err_c = shard_err([(blk, ref[rank * part.block:(rank + 1) * part.block])])
