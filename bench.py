@@ -1084,8 +1084,10 @@ def main_reference(args):
         metric="eval users/s (full-rank top-20)", value=v, unit="users/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
         ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
         data="synthetic", impl="reference",
+        # (the same keys and values as the other arm's `config`: both describe the one job)
         config=dict(workload="full-rank top-20 eval, 1M users x 200k items, d=64 (BASELINE configs[3])", users=job["U"],
-                    items=job["I"], d=job["d"], topk=job["K"], scale=args.scale),
+                    items=job["I"], d=job["d"], topk=job["K"], mask_items_per_user=EVAL_CFG["mask_per_user"],
+                    sharding=f"users/{args.gpus}", l2="flushed between steps (192 MiB write)", scale=args.scale),
         cpu_baseline=dict(value=v, unit="users/s", cores=torch.get_num_threads(), kind="port",
                           sample=f"each step = {n} seeded users of the job against all items (batched reference form + gene_metrics)"),
         e2e=dict(value=v, unit="users/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
